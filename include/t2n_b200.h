@@ -1,0 +1,211 @@
+/*
+ * t2n_b200.h — C ABI of the B200-native TensoRF ray-marching path.
+ *
+ * Drop-in boundary for the hot path of eckertzhang/Text2NeRF.  The reference has no FFI: its
+ * boundary is the Python class surface of models/tensoRF.py:139 `TensorVMSplit`
+ * (TensorBase.forward, models/tensorBase.py:436-507) driven by renderer.py:28-42.  Every entry
+ * point below cites the reference interface it replaces; the Python mirror in
+ * text2nerf_b200/ binds these symbols with ctypes.
+ *
+ * Conventions (following the tree's only native precedent, the vendored SyncBN extension:
+ * `extern "C" int f(raw pointers..., cudaStream_t)`, syncbn.cu:252-266):
+ *   - plain pointers and sizes only, no torch types; all pointers are DEVICE pointers unless
+ *     a comment says otherwise; all floating-point data is fp32;
+ *   - the caller owns every buffer (outputs, saved state, scratch); kernels never allocate and
+ *     never synchronise; work is enqueued on `stream`;
+ *   - return 0 on success, otherwise a cudaError_t value, or a negative T2N_E_* code for an
+ *     argument the library rejects (t2n_error_string explains both);
+ *   - VM factors are passed TEXEL-MAJOR ("channels-last"): plane i is [H][W][C] with
+ *     H = grid[matMode[i][1]], W = grid[matMode[i][0]]; line i is [L][C] with L = grid[vecMode[i]]
+ *     (models/tensoRF.py:150-160 shapes [1,C,H,W] / [1,C,L,1] viewed channels-last).  C % 4 == 0,
+ *     base pointers 16-byte aligned.
+ */
+#ifndef T2N_B200_H
+#define T2N_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* t2n_stream_t;   /* == cudaStream_t */
+
+#define T2N_ABI_VERSION 3
+
+enum {
+    T2N_E_BADARG   = -1,   /* null pointer / non-positive size */
+    T2N_E_LAYOUT   = -2,   /* component count not a multiple of 4, misaligned pointer, too many channels */
+    T2N_E_SHADING  = -3,   /* shading mode / decoder width not supported by the kernels */
+    T2N_E_CAPACITY = -4,   /* R*S does not fit the 31-bit sample-slot index; split the ray batch */
+    T2N_E_DEVICE   = -5    /* not an sm_100 device */
+};
+
+/* shading heads of TensorBase.init_render_func (models/tensorBase.py:200-218) */
+enum {
+    T2N_SHADE_MLP_FEA_NOVIEW = 0,
+    T2N_SHADE_MLP_FEA        = 1,
+    T2N_SHADE_MLP            = 2,
+    T2N_SHADE_SH             = 3,
+    T2N_SHADE_RGB            = 4
+};
+enum { T2N_ACT_SOFTPLUS = 0, T2N_ACT_RELU = 1 };     /* feature2density, tensorBase.py:406-410 */
+
+/* Scalar state of one field = the attributes TensorBase derives in __init__/update_stepSize
+ * (models/tensorBase.py:164-231).  The caller computes inv_aabb and step_size with fp32 tensor
+ * arithmetic exactly as the reference does and passes the resulting values. */
+typedef struct T2NField {
+    float aabb_lo[3], aabb_hi[3];
+    float inv_aabb[3];          /* 2/(hi-lo)                           tensorBase.py:224 */
+    int   grid[3];              /* gridSize (x,y,z)                    tensorBase.py:225 */
+    float step_size;            /* stepSize                            tensorBase.py:227 */
+    float near_clip, far_clip;  /* near_far                            tensorBase.py:307 */
+    float distance_scale;       /*                                     tensorBase.py:475 */
+    float density_shift;        /*                                     tensorBase.py:408 */
+    float weight_thres;         /* rayMarch_weight_thres               tensorBase.py:477 */
+    float eval_z_min;           /* 2.0: eval-only world-z filter       tensorBase.py:459-462 */
+    int   act;                  /* T2N_ACT_*  */
+    int   shading;              /* T2N_SHADE_* */
+    int   app_dim;              /* 27 (3 for RGB)                      tensoRF.py:147 */
+    int   feature_c;            /* decoder width (128), multiple of 16, <= 128 */
+    int   n_sigma[3];           /* density_n_comp                      tensoRF.py:145 */
+    int   n_app[3];             /* appearance_n_comp                   tensoRF.py:146 */
+    int   mlp_in;               /* decoder input width (351 for MLP_Fea_noview fea_pe=6) */
+    int   mlp_in_pad;           /* mlp_in rounded up to a multiple of 32 */
+} T2NField;
+
+/* Parameters (read-only in forward).  State-dict names in comments. */
+typedef struct T2NParams {
+    const float* sigma_plane[3];   /* density_plane.{i}  [H][W][n_sigma[i]] */
+    const float* sigma_line[3];    /* density_line.{i}   [L][n_sigma[i]]    */
+    const float* app_plane[3];     /* app_plane.{i}      [H][W][n_app[i]]   */
+    const float* app_line[3];      /* app_line.{i}       [L][n_app[i]]      */
+    const float* basis;            /* basis_mat.weight   [app_dim][sum n_app] row-major */
+    const float* w1;               /* renderModule.mlp.0.weight [feature_c][mlp_in]  (NULL for SH/RGB) */
+    const float* b1;               /* renderModule.mlp.0.bias   [feature_c] */
+    const float* w2;               /* renderModule.mlp.2.weight [feature_c][feature_c] */
+    const float* b2;
+    const float* w3;               /* renderModule.mlp.4.weight [3][feature_c] */
+    const float* b3;
+    /* Decoder input recipe, built by the host mirror once per shading mode (DESIGN.md "decoder
+     * columns"): the kernels evaluate input columns in pairs; pair q covers internal columns
+     * 2q,2q+1.  pair_desc[q] = srcA | srcB<<8 | freq<<16 | sincos<<20 ; col_perm[k] = the column of
+     * w1 that internal column k multiplies (-1 = zero padding).  Device pointers. */
+    const int32_t* pair_desc;      /* [mlp_in_pad/2] */
+    const int32_t* col_perm;       /* [mlp_in_pad]   */
+} T2NParams;
+
+/* Gradient buffers, same layouts as T2NParams; kernels ACCUMULATE (+=) into them, so the caller
+ * zero-fills (or passes the running .grad buffers).  Replaces autograd through
+ * grid_sampler_2d_backward / addmm for tensorBase.py:467-492. */
+typedef struct T2NGrads {
+    float* sigma_plane[3];
+    float* sigma_line[3];
+    float* app_plane[3];
+    float* app_line[3];
+    float* basis;
+    float* w1; float* b1; float* w2; float* b2; float* w3; float* b3;
+} T2NGrads;
+
+/* Optional occupancy volume = AlphaGridMask (models/tensorBase.py:41-59). */
+typedef struct T2NAlphaMask {
+    const float* volume;        /* [Z][Y][X] fp32 (alpha_volume viewed 3-D), NULL = no mask */
+    int   dims[3];              /* X, Y, Z */
+    float aabb_lo[3];
+    float inv_size[3];          /* invgridSize = 1/(hi-lo)*2, tensorBase.py:48 */
+} T2NAlphaMask;
+
+/* One ray batch.  rays [R][6] = (origin, direction) exactly what renderer.py:33 hands to
+ * tensorf(); jitter [R] = the per-ray U[0,1) offsets the reference draws from the CPU RNG when
+ * is_train (tensorBase.py:313-317), NULL for eval. */
+typedef struct T2NBatch {
+    const float* rays;
+    const float* jitter;
+    int R;
+    int S;                      /* N_samples */
+    int is_train;               /* selects jitter use and disables the eval z filter */
+    int white_bg;               /* effective flag of tensorBase.py:497 (caller resolves the RNG branch) */
+} T2NBatch;
+
+/* Forward outputs = the return tuple of TensorBase.forward (tensorBase.py:507). */
+typedef struct T2NOutputs {
+    float* rgb_map;             /* [R][3] */
+    float* depth_map;           /* [R]    */
+    float* z_vals;              /* [R][S] */
+    float* weight;              /* [R][S] */
+} T2NOutputs;
+
+/* Caller-allocated scratch + state kept for backward.  Sizes in ELEMENTS for a batch (R,S):
+ *   sigma_feat R*S float  (NULL when no backward is needed)  pre-activation density feature,
+ *                                                            -inf where the sample is masked out
+ *   trans      R*S float  (NULL when no backward is needed)  transmittance T_k before sample k
+ *   acc, dsum  R   float                                     sum_k w_k , sum_k w_k z_k
+ *   ray_start, ray_count  R int32                            app-sample segment of each ray
+ *   slots      R*S int32                                     compacted list of samples with
+ *                                                            weight > weight_thres, value r*S+k
+ *   app_rgb    3*R*S float                                   decoder output per listed sample
+ *   counters   8 int32  (zeroed by the library)              [0]=#listed, [1]=#valid sigma samples
+ *   w1_packed  feature_c*mlp_in_pad float                    column-permuted copy of w1
+ *   ray_flags  R int32                                       bit c set iff rgb_map[.,c] was inside
+ *                                                            [0,1] before the clamp (clamp backward)
+ *   w1_grad_packed feature_c*mlp_in_pad float (backward only) gradient of w1_packed
+ * A batch with R*S >= 2^31 is rejected with T2N_E_CAPACITY. */
+typedef struct T2NScratch {
+    float*   sigma_feat;
+    float*   trans;
+    float*   acc;
+    float*   dsum;
+    int32_t* ray_start;
+    int32_t* ray_count;
+    int32_t* slots;
+    float*   app_rgb;
+    int32_t* counters;
+    float*   w1_packed;
+    int32_t* ray_flags;
+    float*   w1_grad_packed;
+} T2NScratch;
+
+/* ---- entry points ------------------------------------------------------------------------ */
+
+int         t2n_abi_version(void);
+const char* t2n_error_string(int code);
+
+/* Number of SMs / device check for the current device (0 on failure). */
+int t2n_device_sm_count(void);
+
+/* Forward render of one ray batch: TensorBase.forward with ndc_ray=False
+ * (models/tensorBase.py:436-507) = sample_ray (:304-323) + compute_densityfeature
+ * (tensoRF.py:205-220) + feature2density + raw2alpha (:19-26) + compute_appfeature
+ * (tensoRF.py:223-239) + renderModule + the reductions of :494-505. */
+int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                       const T2NBatch* batch, const T2NOutputs* out, const T2NScratch* scratch,
+                       t2n_stream_t stream);
+
+/* Backward of the same batch: gradients of a scalar loss given its gradients w.r.t. the three
+ * differentiable outputs (g_weight may be NULL = zeros).  Needs the forward's outputs and
+ * scratch (sigma_feat/trans non-NULL).  Replaces torch autograd over tensorBase.py:436-507. */
+int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                        const T2NBatch* batch, const T2NOutputs* out, const T2NScratch* scratch,
+                        const float* g_rgb_map, const float* g_depth_map, const float* g_weight,
+                        const T2NGrads* grads, t2n_stream_t stream);
+
+/* Camera rays of one view: get_ray_directions (+ optional per-pixel normalisation as
+ * dataLoader/scene_gen.py:45 applies) followed by get_rays (dataLoader/ray_utils.py:24-42,
+ * 66-87).  c2w is a HOST pointer to 12 floats (row-major 3x4).  rays [H*W][6]. */
+int t2n_get_rays(const float* c2w_host, float fx, float fy, float cx, float cy, int H, int W,
+                 int normalize_dirs, float* rays, t2n_stream_t stream);
+
+/* Same, from precomputed camera-space directions [H*W][3] on the device (get_rays proper). */
+int t2n_rotate_rays(const float* c2w_host, const float* directions, int n, float* rays,
+                    t2n_stream_t stream);
+
+/* Density-only query at arbitrary world points: TensorBase.compute_alpha
+ * (models/tensorBase.py:413-433) used by getDenseAlpha/updateAlphaMask.  alpha [n]. */
+int t2n_compute_alpha(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                      const float* xyz, int n, float length, float* alpha, t2n_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2N_B200_H */

@@ -1,0 +1,95 @@
+"""Shared test helpers: golden fixtures, model construction, comparison metrics."""
+import contextlib
+import glob
+import io
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import t2n_oracle as orc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REFERENCE_DIR = "/root/reference"
+
+
+def golden_names(kind=None):
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    names = [n for n in names if n != "get_rays"]
+    if kind == "train":
+        names = [n for n in names if "train" in n]
+    return names
+
+
+class Case:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+        d = json.loads(str(z["spec"]))
+        d.pop("dtype")
+        self.name = name
+        self.spec = orc.FieldSpec(**d)
+        self.params = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+        self.grads = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
+        self.rays = torch.from_numpy(z["rays"])
+        self.is_train = bool(z["is_train"])
+        self.white_bg = bool(z["white_bg"])
+        self.white_eff = bool(z["white_bg_effective"])
+        self.n_samples = int(z["n_samples"])
+        self.jitter = torch.from_numpy(z["jitter"]) if "jitter" in z.files else None
+        self.out = {k: torch.from_numpy(z[k]) for k in ("rgb_map", "depth_map", "z_vals", "weight")}
+        self.alpha = None
+        if "alpha_volume" in z.files:
+            self.alpha = (torch.from_numpy(z["alpha_volume"]), torch.from_numpy(z["alpha_aabb"]))
+        self.rgb_gt = torch.from_numpy(z["rgb_gt"]) if "rgb_gt" in z.files else None
+        self.depth_gt = torch.from_numpy(z["depth_gt"]) if "depth_gt" in z.files else None
+        self.loss = float(z["loss"]) if "loss" in z.files else None
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def build_model(spec: orc.FieldSpec, params, device, alpha=None):
+    """text2nerf_b200.TensorVMSplit with the given state, on `device`."""
+    from text2nerf_b200 import AlphaGridMask, TensorVMSplit
+    with quiet():
+        m = TensorVMSplit(spec.aabb_t().to(device), list(spec.grid), device,
+                          density_n_comp=list(spec.density_n_comp), appearance_n_comp=list(spec.app_n_comp),
+                          app_dim=spec.app_dim, near_far=list(spec.near_far), shadingMode=spec.shading,
+                          alphaMask_thres=0.001, density_shift=spec.density_shift,
+                          distance_scale=spec.distance_scale, pos_pe=spec.pos_pe, view_pe=spec.view_pe,
+                          fea_pe=spec.fea_pe, featureC=spec.featureC, step_ratio=spec.step_ratio,
+                          fea2denseAct=spec.act)
+    m.load_state_dict({k: v.to(device) for k, v in params.items()})
+    if alpha is not None:
+        vol, maabb = alpha
+        m.alphaMask = AlphaGridMask(device, maabb.to(device), vol[0, 0].to(device))
+    return m
+
+
+def render_with_jitter(model, rays, jitter, is_train, white_bg_effective, n_samples):
+    """Call the kernel path with an explicit per-ray jitter (what tensorBase.forward would have
+    drawn from the CPU RNG), bypassing the RNG draw of TensorBase.forward."""
+    from text2nerf_b200.tensorBase import _RenderFn
+    S = n_samples if n_samples > 0 else model.nSamples
+    jit = None if jitter is None else jitter.reshape(-1).to(rays.device).contiguous()
+    return _RenderFn.apply(model, rays.contiguous(), jit, S, bool(is_train), bool(white_bg_effective),
+                           *model._flat_params())
+
+
+def rel_err(a, b, floor=0.0):
+    """max |a-b| / max(|b|, floor)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return float(((a - b).abs() / b.abs().clamp_min(floor)).max()) if a.numel() else 0.0
+
+
+def scaled_err(a, b):
+    """max |a-b| / max |b| : error relative to the tensor's scale."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) if a.numel() else 0.0
+
+
+def cosine(a, b):
+    a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))

@@ -1,0 +1,317 @@
+// C-ABI entry points of libt2n_b200.so (declared in include/t2n_b200.h).
+// Host-side argument checking, launch configuration and kernel dispatch; no allocation, no sync.
+#include <cstdio>
+#include <cstring>
+#include "launch.h"
+#include "rays.cuh"
+
+using namespace t2n;
+
+namespace {
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int cc_major = 0;
+    bool ok = false;
+};
+
+DeviceInfo& device_info() {
+    static thread_local DeviceInfo info[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DeviceInfo& d = info[dev & 63];
+    if (!d.ok) {
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+        d.ok = d.sm_count > 0;
+    }
+    return d;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_field(const T2NField* f, const T2NParams* p) {
+    if (!f || !p) return T2N_E_BADARG;
+    for (int i = 0; i < 3; ++i) {
+        if (f->grid[i] < 2) return T2N_E_BADARG;
+        if (f->n_sigma[i] <= 0 || f->n_sigma[i] % 4 || f->n_sigma[i] > 64) return T2N_E_LAYOUT;
+        if (f->n_app[i] <= 0 || f->n_app[i] % 4 || f->n_app[i] > 64) return T2N_E_LAYOUT;
+        if (!p->sigma_plane[i] || !p->sigma_line[i] || !p->app_plane[i] || !p->app_line[i]) return T2N_E_BADARG;
+        if (!aligned16(p->sigma_plane[i]) || !aligned16(p->sigma_line[i]) || !aligned16(p->app_plane[i]) ||
+            !aligned16(p->app_line[i]))
+            return T2N_E_LAYOUT;
+    }
+    if (!p->basis) return T2N_E_BADARG;
+    if (f->shading < T2N_SHADE_MLP_FEA_NOVIEW || f->shading > T2N_SHADE_RGB) return T2N_E_SHADING;
+    if (f->shading <= T2N_SHADE_MLP) {
+        if (f->feature_c < 16 || f->feature_c > 128 || f->feature_c % 16) return T2N_E_SHADING;
+        if (f->mlp_in <= 0 || f->mlp_in_pad % 32 || f->mlp_in_pad < f->mlp_in || f->mlp_in_pad > 512) return T2N_E_SHADING;
+        if (f->app_dim + 7 > 255) return T2N_E_SHADING;
+        if (!p->w1 || !p->b1 || !p->w2 || !p->b2 || !p->w3 || !p->b3 || !p->pair_desc || !p->col_perm) return T2N_E_BADARG;
+        if (!aligned16(p->w2)) return T2N_E_LAYOUT;
+    } else if (f->shading == T2N_SHADE_SH) {
+        if (f->app_dim != 27) return T2N_E_SHADING;
+    } else if (f->app_dim != 3) {
+        return T2N_E_SHADING;
+    }
+    if ((f->n_app[0] + f->n_app[1] + f->n_app[2]) % 4) return T2N_E_LAYOUT;
+    return 0;
+}
+
+FieldDev make_field_dev(const T2NField* f, const T2NAlphaMask* mask) {
+    FieldDev d;
+    memset(&d, 0, sizeof(d));
+    for (int a = 0; a < 3; ++a) {
+        d.lo[a] = f->aabb_lo[a]; d.hi[a] = f->aabb_hi[a]; d.inv[a] = f->inv_aabb[a];
+        d.G[a] = f->grid[a];
+        d.hgm1[a] = 0.5f * (float)(f->grid[a] - 1);
+    }
+    d.step = f->step_size; d.near_clip = f->near_clip; d.far_clip = f->far_clip;
+    d.dist_scale = f->distance_scale; d.dens_shift = f->density_shift; d.w_thres = f->weight_thres;
+    d.z_min = f->eval_z_min; d.act = f->act;
+    d.mask = nullptr;
+    if (mask && mask->volume) {
+        d.mask = mask->volume;
+        for (int a = 0; a < 3; ++a) { d.mdim[a] = mask->dims[a]; d.mlo[a] = mask->aabb_lo[a]; d.minv[a] = mask->inv_size[a]; }
+    }
+    return d;
+}
+
+int max_quads(const int n[3]) {
+    int m = n[0] > n[1] ? n[0] : n[1];
+    m = m > n[2] ? m : n[2];
+    return (m + 15) / 16;
+}
+
+#define T2N_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+AppArgs make_app_args(const T2NField* f, const T2NParams* p, const FieldDev& fd, const T2NBatch* b,
+                      const T2NOutputs* out, const T2NScratch* s) {
+    AppArgs a;
+    memset(&a, 0, sizeof(a));
+    a.f = fd;
+    int off = 0;
+    for (int i = 0; i < 3; ++i) {
+        a.ap[i] = p->app_plane[i]; a.al[i] = p->app_line[i]; a.ac[i] = f->n_app[i];
+        a.aoff[i] = off; off += f->n_app[i];
+    }
+    a.n_app_total = off;
+    a.app_dim = f->app_dim;
+    a.shading = f->shading;
+    a.C = f->shading <= T2N_SHADE_MLP ? f->feature_c : 16;
+    a.Kp = f->shading <= T2N_SHADE_MLP ? f->mlp_in_pad : 32;
+    a.basis = p->basis;
+    a.w1p = s->w1_packed; a.b1 = p->b1; a.w2 = p->w2; a.b2 = p->b2; a.w3 = p->w3; a.b3 = p->b3;
+    a.pair_desc = p->pair_desc;
+    a.rays = b->rays; a.z_vals = out->z_vals; a.slots = s->slots; a.counters = s->counters; a.S = b->S;
+    a.app_rgb = s->app_rgb;
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int t2n_abi_version(void) { return T2N_ABI_VERSION; }
+
+const char* t2n_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case T2N_E_BADARG: return "t2n: null pointer or non-positive size";
+        case T2N_E_LAYOUT: return "t2n: factor layout rejected (channels % 4, > 64 channels, or pointer not 16-byte aligned)";
+        case T2N_E_SHADING: return "t2n: shading mode / decoder shape not supported by the kernels";
+        case T2N_E_CAPACITY: return "t2n: R*S exceeds the 31-bit sample-slot index; split the ray batch";
+        case T2N_E_DEVICE: return "t2n: current device is not sm_100";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "t2n: unknown error";
+    }
+}
+
+int t2n_device_sm_count(void) {
+    DeviceInfo& d = device_info();
+    return d.ok ? d.sm_count : 0;
+}
+
+int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                       const T2NBatch* batch, const T2NOutputs* out, const T2NScratch* scratch,
+                       t2n_stream_t stream) {
+    int rc = check_field(field, params);
+    if (rc) return rc;
+    if (!batch || !out || !scratch || !batch->rays || batch->R <= 0 || batch->S <= 0) return T2N_E_BADARG;
+    if (batch->is_train && !batch->jitter) return T2N_E_BADARG;
+    if (!out->rgb_map || !out->depth_map || !out->z_vals || !out->weight) return T2N_E_BADARG;
+    if (!scratch->acc || !scratch->dsum || !scratch->ray_start || !scratch->ray_count || !scratch->slots ||
+        !scratch->app_rgb || !scratch->counters)
+        return T2N_E_BADARG;
+    if ((long long)batch->R * batch->S >= (1ll << 31)) return T2N_E_CAPACITY;
+    DeviceInfo& dev = device_info();
+    if (!dev.ok || dev.cc_major != 10) return T2N_E_DEVICE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool mlp = field->shading <= T2N_SHADE_MLP;
+    if (mlp && !scratch->w1_packed) return T2N_E_BADARG;
+
+    const FieldDev fd = make_field_dev(field, mask);
+    T2N_CUDA(cudaMemsetAsync(scratch->counters, 0, 8 * sizeof(int32_t), st));
+
+    // ---- K1
+    MarchArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.f = fd;
+    int line_bytes = 0;
+    for (int i = 0; i < 3; ++i) {
+        ma.sp[i] = params->sigma_plane[i]; ma.sl[i] = params->sigma_line[i]; ma.sc[i] = field->n_sigma[i];
+        line_bytes += field->grid[2 - i] * field->n_sigma[i] * 4;
+    }
+    ma.rays = batch->rays; ma.jitter = batch->jitter; ma.R = batch->R; ma.S = batch->S;
+    ma.is_train = batch->is_train;
+    ma.lines_in_smem = line_bytes <= 96 * 1024;
+    if (!ma.lines_in_smem) line_bytes = 0;
+    ma.z_vals = out->z_vals; ma.weight = out->weight; ma.sigma_feat = scratch->sigma_feat; ma.trans = scratch->trans;
+    ma.acc = scratch->acc; ma.dsum = scratch->dsum; ma.ray_start = scratch->ray_start; ma.ray_count = scratch->ray_count;
+    ma.slots = scratch->slots; ma.counters = scratch->counters;
+    {
+        const int warps_needed = batch->R;
+        int ctas_per_sm = line_bytes > 0 ? (int)((220 * 1024) / (line_bytes + 1024)) : 4;
+        ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+        int grid = dev.sm_count * ctas_per_sm;
+        const int need = (warps_needed + 7) / 8;
+        if (grid > need) grid = need;
+        rc = launch_march(ma, max_quads(field->n_sigma), line_bytes, grid, st);
+        if (rc) return rc;
+    }
+
+    // ---- K2
+    if (mlp) {
+        rc = launch_pack_w1(params->w1, params->col_perm, field->feature_c, field->mlp_in, field->mlp_in_pad,
+                            scratch->w1_packed, st);
+        if (rc) return rc;
+    }
+    {
+        AppArgs aa = make_app_args(field, params, fd, batch, out, scratch);
+        const AppSmem L = app_smem_layout(aa.n_app_total, aa.app_dim, aa.C, aa.Kp);
+        const int smem_bytes = L.total * 4;
+        if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
+        const int grid = dev.sm_count;
+        rc = launch_app_forward(aa, max_quads(field->n_app), smem_bytes, grid, st);
+        if (rc) return rc;
+    }
+
+    // ---- K3
+    {
+        FinalizeArgs fa;
+        fa.rays = batch->rays; fa.weight = out->weight; fa.app_rgb = scratch->app_rgb; fa.slots = scratch->slots;
+        fa.ray_start = scratch->ray_start; fa.ray_count = scratch->ray_count; fa.acc = scratch->acc; fa.dsum = scratch->dsum;
+        fa.rgb_map = out->rgb_map; fa.depth_map = out->depth_map; fa.ray_flags = scratch->ray_flags; fa.R = batch->R; fa.white_bg = batch->white_bg;
+        rc = launch_finalize(fa, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                        const T2NBatch* batch, const T2NOutputs* out, const T2NScratch* scratch,
+                        const float* g_rgb_map, const float* g_depth_map, const float* g_weight,
+                        const T2NGrads* grads, t2n_stream_t stream) {
+    int rc = check_field(field, params);
+    if (rc) return rc;
+    if (!batch || !out || !scratch || !grads || !g_rgb_map || !g_depth_map) return T2N_E_BADARG;
+    if (!scratch->sigma_feat || !scratch->trans || !scratch->ray_flags) return T2N_E_BADARG;
+    DeviceInfo& dev = device_info();
+    if (!dev.ok || dev.cc_major != 10) return T2N_E_DEVICE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const FieldDev fd = make_field_dev(field, mask);
+    const bool mlp = field->shading <= T2N_SHADE_MLP;
+    // ---- appearance backward first (it only needs forward state), then the ray sweep
+    {
+        AppBwdArgs b;
+        memset(&b, 0, sizeof(b));
+        b.fw = make_app_args(field, params, fd, batch, out, scratch);
+        for (int i = 0; i < 3; ++i) {
+            b.gap[i] = grads->app_plane[i]; b.gal[i] = grads->app_line[i];
+            if (!b.gap[i] || !b.gal[i]) return T2N_E_BADARG;
+        }
+        b.weight = out->weight; b.ray_flags = scratch->ray_flags; b.g_rgb = g_rgb_map;
+        b.g_basis = grads->basis; b.g_w1p = scratch->w1_grad_packed; b.g_b1 = grads->b1; b.g_w2 = grads->w2;
+        b.g_b2 = grads->b2; b.g_w3 = grads->w3; b.g_b3 = grads->b3;
+        if (!grads->basis) return T2N_E_BADARG;
+        if (mlp) {
+            if (!scratch->w1_grad_packed || !scratch->w1_packed || !grads->w1 || !grads->b1 || !grads->w2 || !grads->b2 ||
+                !grads->w3 || !grads->b3)
+                return T2N_E_BADARG;
+            T2N_CUDA(cudaMemsetAsync(scratch->w1_grad_packed, 0, (size_t)b.fw.C * b.fw.Kp * sizeof(float), st));
+        }
+        const AppBwdSmem BL = app_bwd_smem_layout(b.fw.n_app_total, b.fw.app_dim, b.fw.C, b.fw.Kp);
+        const int smem = BL.total * 4;
+        if (smem > dev.max_smem_optin) return T2N_E_SHADING;
+        rc = launch_app_backward(b, max_quads(field->n_app), smem, dev.sm_count, st);
+        if (rc) return rc;
+        if (mlp) {
+            rc = launch_unpack_w1_grad(scratch->w1_grad_packed, params->col_perm, b.fw.C, field->mlp_in, b.fw.Kp, grads->w1, st);
+            if (rc) return rc;
+        }
+    }
+    // ---- ray sweep + density scatter
+    {
+        RayBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.f = fd;
+        int line_bytes = 0;
+        for (int i = 0; i < 3; ++i) {
+            a.sp[i] = params->sigma_plane[i]; a.sl[i] = params->sigma_line[i]; a.sc[i] = field->n_sigma[i];
+            a.gsp[i] = grads->sigma_plane[i]; a.gsl[i] = grads->sigma_line[i];
+            if (!a.gsp[i] || !a.gsl[i]) return T2N_E_BADARG;
+            line_bytes += field->grid[2 - i] * field->n_sigma[i] * 4;
+        }
+        a.rays = batch->rays; a.R = batch->R; a.S = batch->S; a.white_bg = batch->white_bg;
+        a.lines_in_smem = line_bytes <= 96 * 1024;
+        if (!a.lines_in_smem) line_bytes = 0;
+        a.z_vals = out->z_vals; a.weight = out->weight; a.sigma_feat = scratch->sigma_feat; a.trans = scratch->trans;
+        a.ray_start = scratch->ray_start; a.ray_count = scratch->ray_count; a.ray_flags = scratch->ray_flags;
+        a.app_rgb = scratch->app_rgb; a.g_rgb = g_rgb_map; a.g_depth = g_depth_map; a.g_weight = g_weight;
+        int ctas_per_sm = line_bytes > 0 ? (int)((220 * 1024) / (line_bytes + 1024)) : 4;
+        ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+        int grid = dev.sm_count * ctas_per_sm;
+        const int need = (batch->R + 7) / 8;
+        if (grid > need) grid = need;
+        rc = launch_ray_backward(a, max_quads(field->n_sigma), line_bytes, grid, st);
+    }
+    return rc;
+}
+
+int t2n_get_rays(const float* c2w_host, float fx, float fy, float cx, float cy, int H, int W,
+                 int normalize_dirs, float* rays, t2n_stream_t stream) {
+    if (!c2w_host || !rays || H <= 0 || W <= 0) return T2N_E_BADARG;
+    Pose P;
+    memcpy(P.m, c2w_host, sizeof(P.m));
+    const int n = H * W;
+    rays_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, fx, fy, cx, cy, H, W,
+                                                                                 normalize_dirs, rays);
+    return (int)cudaGetLastError();
+}
+
+int t2n_rotate_rays(const float* c2w_host, const float* directions, int n, float* rays, t2n_stream_t stream) {
+    if (!c2w_host || !directions || !rays || n <= 0) return T2N_E_BADARG;
+    Pose P;
+    memcpy(P.m, c2w_host, sizeof(P.m));
+    rotate_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, directions, n, rays);
+    return (int)cudaGetLastError();
+}
+
+int t2n_compute_alpha(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                      const float* xyz, int n, float length, float* alpha, t2n_stream_t stream) {
+    if (!field || !params || !xyz || !alpha || n <= 0) return T2N_E_BADARG;
+    for (int i = 0; i < 3; ++i) {
+        if (field->n_sigma[i] % 4) return T2N_E_LAYOUT;
+        if (!params->sigma_plane[i] || !params->sigma_line[i]) return T2N_E_BADARG;
+    }
+    AlphaArgs a;
+    memset(&a, 0, sizeof(a));
+    a.f = make_field_dev(field, mask);
+    for (int i = 0; i < 3; ++i) { a.sp[i] = params->sigma_plane[i]; a.sl[i] = params->sigma_line[i]; a.sc[i] = field->n_sigma[i]; }
+    a.xyz = xyz; a.n = n; a.length = length; a.alpha = alpha;
+    alpha_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

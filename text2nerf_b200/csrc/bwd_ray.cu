@@ -1,0 +1,21 @@
+// ray sweep backward launcher
+#include "launch.h"
+namespace t2n {
+template <int NQ>
+static int go(const RayBwdArgs& a, int smem, int grid, cudaStream_t st) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ray_backward_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    ray_backward_kernel<NQ><<<grid, 256, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+int launch_ray_backward(const RayBwdArgs& a, int nq, int smem, int grid, cudaStream_t st) {
+    switch (nq) {
+        case 1: return go<1>(a, smem, grid, st);
+        case 2: return go<2>(a, smem, grid, st);
+        case 3: return go<3>(a, smem, grid, st);
+        default: return go<4>(a, smem, grid, st);
+    }
+}
+}  // namespace t2n

@@ -1,0 +1,17 @@
+// Host-side launchers implemented one translation unit per kernel family (parallel build).
+#pragma once
+#include "common.cuh"
+#include "march.cuh"
+#include "appearance.cuh"
+#include "backward.cuh"
+
+
+namespace t2n {
+int launch_march(const MarchArgs& a, int nq, int line_bytes, int grid, cudaStream_t st);
+int launch_finalize(const FinalizeArgs& a, cudaStream_t st);
+int launch_app_forward(const AppArgs& a, int nq, int smem_bytes, int grid, cudaStream_t st);
+int launch_pack_w1(const float* w1, const int32_t* perm, int C, int K, int Kp, float* w1p, cudaStream_t st);
+int launch_ray_backward(const RayBwdArgs& a, int nq, int smem_bytes, int grid, cudaStream_t st);
+int launch_app_backward(const AppBwdArgs& a, int nq, int smem_bytes, int grid, cudaStream_t st);
+int launch_unpack_w1_grad(const float* gw1p, const int32_t* perm, int C, int K, int Kp, float* gw1, cudaStream_t st);
+}  // namespace t2n

@@ -1,0 +1,38 @@
+"""Host-side mirror of the render driver of the reference's ``renderer.py``:
+SimpleSampler (:14-26) and OctreeRender_trilinear_fast (:28-42).  Same signatures and return
+tuple; each chunk is one fused-kernel forward of the model.  The chunk loop and the final
+concatenation are kept because callers rely on the 5-tuple of dense [N,S] tensors."""
+import numpy as np
+import torch
+
+from .tensoRF import AlphaGridMask, TensorCP, TensorVM, TensorVMSplit, raw2alpha  # noqa: F401 (re-exported like the reference)
+
+
+class SimpleSampler:
+    """Epoch-wise random permutation of `total` ray indices served in `batch`-sized slices."""
+
+    def __init__(self, total, batch):
+        self.total = total
+        self.batch = batch
+        self.curr = total
+        self.ids = None
+
+    def nextids(self):
+        self.curr += self.batch
+        if self.curr + self.batch > self.total:
+            self.ids = torch.LongTensor(np.random.permutation(self.total))
+            self.curr = 0
+        return self.ids[self.curr:self.curr + self.batch]
+
+
+def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray=False, white_bg=True,
+                                is_train=False, device='cuda'):
+    n_rays = rays.shape[0]
+    parts = ([], [], [], [])
+    for start in range(0, n_rays, chunk):
+        rays_chunk = rays[start:start + chunk].to(device)
+        out = tensorf(rays_chunk, is_train=is_train, white_bg=white_bg, ndc_ray=ndc_ray, N_samples=N_samples)
+        for acc, t in zip(parts, out):
+            acc.append(t)
+    rgbs, depth_maps, z_val, weights = (torch.cat(p) for p in parts)
+    return rgbs, None, depth_maps, weights, z_val

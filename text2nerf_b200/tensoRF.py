@@ -1,0 +1,270 @@
+"""Host-side mirror of the reference's ``models/tensoRF.py``: TensorVMSplit
+(models/tensoRF.py:139-303) on top of the kernel-backed TensorBase.
+
+Parameters keep the reference's names and shapes ([1,C,H,W] planes, [1,C,L,1] lines,
+``basis_mat``, ``renderModule.mlp.*``) so checkpoints and optimisers are interchangeable, but
+the plane/line tensors are stored ``channels_last`` -- physically [H][W][C] -- which is the
+texel-major layout the gather kernels read with 16-byte vector loads.  Shapes, state-dict
+keys and Adam semantics are unchanged ("layout trick").
+
+TensorVM and TensorCP are exported as names only (renderer.py imports them): the reference's
+TensorVM is dead code (calls a missing method, tensoRF.py:135) and TensorCP is outside the
+north-star path; instantiating either raises.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import _native as nat
+from .tensorBase import (AlphaGridMask, TensorBase, _texel_major, positional_encoding, raw2alpha)  # noqa: F401
+
+_CL = torch.channels_last
+
+
+def _as_list3(n) -> List[int]:
+    return [int(n)] * 3 if isinstance(n, int) else [int(v) for v in n]
+
+
+class _NotBuilt(torch.nn.Module):
+    def __init__(self, *a, **k):
+        super().__init__()
+        raise NotImplementedError(f"{type(self).__name__} is outside the B200 hot-path scope (SURVEY.md 2.1 row 2); "
+                                  "use TensorVMSplit")
+
+
+class TensorVM(_NotBuilt):
+    pass
+
+
+class TensorCP(_NotBuilt):
+    pass
+
+
+class TensorVMSplit(TensorBase):
+    def __init__(self, aabb, gridSize, device, **kargs):
+        super().__init__(aabb, gridSize, device, **kargs)
+
+    # ---- parameters --------------------------------------------------------------------------------
+    def init_svd_volume(self, res, device):
+        self.density_n_comp = _as_list3(self.density_n_comp)
+        self.app_n_comp = _as_list3(self.app_n_comp)
+        self.density_plane, self.density_line = self.init_one_svd(self.density_n_comp, self.gridSize, 0.1, device)
+        self.app_plane, self.app_line = self.init_one_svd(self.app_n_comp, self.gridSize, 0.1, device)
+        self.basis_mat = torch.nn.Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
+
+    def init_one_svd(self, n_component, gridSize, scale, device):
+        """0.1*randn factors drawn in the reference's order (plane_i, line_i for i=0,1,2 -- so the
+        same torch seed gives the same field, tensoRF.py:150-160), stored channels-last."""
+        planes, lines = [], []
+        for i in range(3):
+            a0, a1 = self.matMode[i]
+            v = self.vecMode[i]
+            plane = scale * torch.randn((1, n_component[i], int(gridSize[a1]), int(gridSize[a0])))
+            line = scale * torch.randn((1, n_component[i], int(gridSize[v]), 1))
+            planes.append(torch.nn.Parameter(plane.to(device).contiguous(memory_format=_CL)))
+            lines.append(torch.nn.Parameter(line.to(device).contiguous(memory_format=_CL)))
+        return torch.nn.ParameterList(planes), torch.nn.ParameterList(lines)
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
+        groups = [{'params': self.density_line, 'lr': lr_init_spatialxyz},
+                  {'params': self.density_plane, 'lr': lr_init_spatialxyz},
+                  {'params': self.app_line, 'lr': lr_init_spatialxyz},
+                  {'params': self.app_plane, 'lr': lr_init_spatialxyz},
+                  {'params': self.basis_mat.parameters(), 'lr': lr_init_network}]
+        if isinstance(self.renderModule, torch.nn.Module):
+            groups.append({'params': self.renderModule.parameters(), 'lr': lr_init_network})
+        return groups
+
+    # ---- regularisers (parameter-only, dense streaming work; tensoRF.py:173-203) -------------------
+    def vectorDiffs(self, vector_comps):
+        total = 0
+        for comp in vector_comps:
+            n_comp, n_size = comp.shape[1:-1]
+            flat = comp.reshape(n_comp, n_size)
+            gram = flat @ flat.t()
+            off_diag = gram.reshape(-1)[1:].view(n_comp - 1, n_comp + 1)[..., :-1]
+            total = total + off_diag.abs().mean()
+        return total
+
+    def vector_comp_diffs(self):
+        return self.vectorDiffs(self.density_line) + self.vectorDiffs(self.app_line)
+
+    def density_L1(self):
+        total = 0
+        for plane, line in zip(self.density_plane, self.density_line):
+            total = total + plane.abs().mean() + line.abs().mean()
+        return total
+
+    def TV_loss_density(self, reg):
+        total = 0
+        for plane in self.density_plane:
+            total = total + reg(plane) * 1e-2
+        return total
+
+    def TV_loss_app(self, reg):
+        total = 0
+        for plane in self.app_plane:
+            total = total + reg(plane) * 1e-2
+        return total
+
+    # ---- factor lookups as tensor ops (API parity; the render path gathers inside the kernels) -----
+    def _vm_grids(self, xyz_sampled):
+        planes = torch.stack([xyz_sampled[..., self.matMode[i]] for i in range(3)]).detach().view(3, -1, 1, 2)
+        lines = torch.stack([xyz_sampled[..., self.vecMode[i]] for i in range(3)])
+        lines = torch.stack((torch.zeros_like(lines), lines), dim=-1).detach().view(3, -1, 1, 2)
+        return planes, lines
+
+    def compute_densityfeature(self, xyz_sampled):
+        gp, gl = self._vm_grids(xyz_sampled)
+        n = xyz_sampled.shape[0]
+        feat = torch.zeros((n,), device=xyz_sampled.device)
+        for i in range(3):
+            pv = F.grid_sample(self.density_plane[i], gp[[i]], align_corners=True).view(-1, n)
+            lv = F.grid_sample(self.density_line[i], gl[[i]], align_corners=True).view(-1, n)
+            feat = feat + (pv * lv).sum(0)
+        return feat
+
+    def compute_appfeature(self, xyz_sampled):
+        gp, gl = self._vm_grids(xyz_sampled)
+        n = xyz_sampled.shape[0]
+        pv = torch.cat([F.grid_sample(self.app_plane[i], gp[[i]], align_corners=True).view(-1, n) for i in range(3)])
+        lv = torch.cat([F.grid_sample(self.app_line[i], gl[[i]], align_corners=True).view(-1, n) for i in range(3)])
+        return self.basis_mat((pv * lv).T)
+
+    # ---- grid maintenance (tensoRF.py:243-303) -----------------------------------------------------
+    @torch.no_grad()
+    def up_sampling_VM(self, plane_coef, line_coef, res_target):
+        for i in range(3):
+            a0, a1 = self.matMode[i]
+            v = self.vecMode[i]
+            p = F.interpolate(plane_coef[i].data, size=(res_target[a1], res_target[a0]), mode='bilinear', align_corners=True)
+            l = F.interpolate(line_coef[i].data, size=(res_target[v], 1), mode='bilinear', align_corners=True)
+            plane_coef[i] = torch.nn.Parameter(p.contiguous(memory_format=_CL))
+            line_coef[i] = torch.nn.Parameter(l.contiguous(memory_format=_CL))
+        return plane_coef, line_coef
+
+    @torch.no_grad()
+    def upsample_volume_grid(self, res_target):
+        self.app_plane, self.app_line = self.up_sampling_VM(self.app_plane, self.app_line, res_target)
+        self.density_plane, self.density_line = self.up_sampling_VM(self.density_plane, self.density_line, res_target)
+        self.update_stepSize(res_target)
+        print(f'upsamping to {res_target}')
+
+    @torch.no_grad()
+    def shrink(self, new_aabb):
+        print("====> shrinking ...")
+        xyz_min, xyz_max = new_aabb
+        lo = (xyz_min - self.aabb[0]) / self.units
+        hi = (xyz_max - self.aabb[0]) / self.units
+        lo, hi = torch.round(torch.round(lo)).long(), torch.round(hi).long() + 1
+        hi = torch.stack([hi, self.gridSize]).amin(0)
+        for i in range(3):
+            v = self.vecMode[i]
+            a0, a1 = self.matMode[i]
+            for lines in (self.density_line, self.app_line):
+                lines[i] = torch.nn.Parameter(lines[i].data[..., lo[v]:hi[v], :].contiguous(memory_format=_CL))
+            for planes in (self.density_plane, self.app_plane):
+                planes[i] = torch.nn.Parameter(
+                    planes[i].data[..., lo[a1]:hi[a1], lo[a0]:hi[a0]].contiguous(memory_format=_CL))
+        if not torch.all(self.alphaMask.gridSize == self.gridSize):
+            t_lo, t_hi = lo / (self.gridSize - 1), (hi - 1) / (self.gridSize - 1)
+            fixed = torch.zeros_like(new_aabb)
+            fixed[0] = (1 - t_lo) * self.aabb[0] + t_lo * self.aabb[1]
+            fixed[1] = (1 - t_hi) * self.aabb[0] + t_hi * self.aabb[1]
+            print("aabb", new_aabb, "\ncorrect aabb", fixed)
+            new_aabb = fixed
+        new_size = hi - lo
+        self.aabb = new_aabb
+        self.update_stepSize((int(new_size[0]), int(new_size[1]), int(new_size[2])))
+
+    # ---- native glue -------------------------------------------------------------------------------
+    def _flat_params(self) -> List[torch.Tensor]:
+        """Parameter order of the C ABI structs: sigma planes, sigma lines, app planes, app lines,
+        basis, then the decoder's six tensors."""
+        ps = list(self.density_plane) + list(self.density_line) + list(self.app_plane) + list(self.app_line)
+        ps.append(self.basis_mat.weight)
+        if self._is_mlp:
+            m = self.renderModule.mlp
+            ps += [m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias]
+        return ps
+
+    def _native_param_tensors(self, params: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        out = []
+        for j, p in enumerate(params):
+            p = p.detach()
+            if p.dtype != torch.float32:
+                raise TypeError("text2nerf_b200 parameters must be float32")
+            out.append(_texel_major(p) if j < 12 else p.contiguous())
+        return out
+
+    def _native_params(self, p_cl: Sequence[torch.Tensor]) -> nat.T2NParams:
+        s = nat.T2NParams()
+        s.sigma_plane = nat.P3(*[t.data_ptr() for t in p_cl[0:3]])
+        s.sigma_line = nat.P3(*[t.data_ptr() for t in p_cl[3:6]])
+        s.app_plane = nat.P3(*[t.data_ptr() for t in p_cl[6:9]])
+        s.app_line = nat.P3(*[t.data_ptr() for t in p_cl[9:12]])
+        s.basis = p_cl[12].data_ptr()
+        if self._is_mlp:
+            s.w1, s.b1, s.w2, s.b2, s.w3, s.b3 = [t.data_ptr() for t in p_cl[13:19]]
+            perm, pairs = self._recipe_tensors(p_cl[12].device)
+            s.col_perm, s.pair_desc = perm.data_ptr(), pairs.data_ptr()
+        return s
+
+    def _grad_buffers(self, p_cl: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """Zero-filled gradient buffers in the parameters' own memory layout.  With
+        enable_flat_grads() they are views into one flat fp32 buffer (the NCCL all-reduce buffer)."""
+        flat = getattr(self, "_flat_grad", None)
+        if flat is not None:
+            return flat["views"]            # the trainer zeroes the flat buffer once per step
+        return [torch.zeros_like(t) for t in p_cl]
+
+    def _native_grads(self, grads: Sequence[torch.Tensor]) -> nat.T2NGrads:
+        g = nat.T2NGrads()
+        g.sigma_plane = nat.P3(*[t.data_ptr() for t in grads[0:3]])
+        g.sigma_line = nat.P3(*[t.data_ptr() for t in grads[3:6]])
+        g.app_plane = nat.P3(*[t.data_ptr() for t in grads[6:9]])
+        g.app_line = nat.P3(*[t.data_ptr() for t in grads[9:12]])
+        g.basis = grads[12].data_ptr()
+        if self._is_mlp:
+            g.w1, g.b1, g.w2, g.b2, g.w3, g.b3 = [t.data_ptr() for t in grads[13:19]]
+        return g
+
+    def _grads_for_autograd(self, grads: Sequence[torch.Tensor]):
+        if getattr(self, "_flat_grad", None) is not None:
+            # flat mode: the data gradients live in the flat buffer (all-reduced by the trainer and
+            # attached to .grad afterwards, text2nerf_b200/dist.py); autograd gets nothing
+            return (None,) * len(grads)
+        return tuple(grads)
+
+    def enable_flat_grads(self, on: bool = True):
+        """Back every data gradient by ONE flat fp32 buffer (planes, lines, basis, decoder), laid
+        out in the C-ABI parameter order.  The ray-sharded trainer all-reduces this buffer with a
+        single NCCL call per step (text2nerf_b200/dist.py).  While enabled, backward ACCUMULATES
+        into the buffer and hands autograd no parameter gradients: the caller zeroes the buffer
+        at the start of a step and attaches the views to .grad after the all-reduce."""
+        if not on:
+            self._flat_grad = None
+            return None
+        params = self._flat_params()
+        p_cl = self._native_param_tensors(params)
+        sizes = [t.numel() for t in p_cl]
+        # keep every segment 16-byte aligned for the vector atomics
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += (n + 3) & ~3
+        buf = torch.zeros((o,), device=p_cl[0].device, dtype=torch.float32)
+        views = []
+        for t, off, n in zip(p_cl, offs, sizes):
+            views.append(torch.as_strided(buf, t.shape, t.stride(), off))
+        self._flat_grad = {"buffer": buf, "views": views}
+        return buf
+
+    def app_sample_count(self) -> int:
+        """Samples that passed the weight threshold / the validity test in the last forward
+        (device->host read; diagnostics and roofline accounting only)."""
+        c = self._last_counters
+        return (0, 0) if c is None else tuple(int(v) for v in c[:2].tolist())

@@ -1,0 +1,637 @@
+"""Host-side mirror of the reference's ``models/tensorBase.py`` operator surface.
+
+Same names, constructor arguments, attributes, state-dict keys and error behaviour as
+TensorBase / AlphaGridMask / the MLPRender_* heads (models/tensorBase.py:29-507), so that
+renderer.py and text2nerf_main.py can use the classes unchanged -- but ``forward`` is ONE call
+into the hand-written sm_100a kernels of libt2n_b200.so through the C ABI
+(include/t2n_b200.h), wrapped in a torch.autograd.Function.  PyTorch is used for device
+memory, streams and autograd plumbing only; there is no PyTorch/CPU fallback for the path.
+
+Maintenance methods that are not on the per-ray hot path (alpha-mask update, shrink,
+upsampling, TV/L1 regularisers, ray filtering) are written with torch tensor ops on the
+module's device, as SURVEY.md section 7 step 2 plans.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn
+import torch.nn.functional as F
+
+from . import _native as nat
+from .sh import eval_sh_bases
+
+SHADE_IDS = {"MLP_Fea_noview": 0, "MLP_Fea": 1, "MLP": 2, "SH": 3, "RGB": 4}
+_CL = torch.channels_last
+
+
+# ------------------------------------------------------------------------------------------------
+# small functional pieces the reference exports from this module
+# ------------------------------------------------------------------------------------------------
+def positional_encoding(positions, freqs):
+    """sin/cos frequency encoding, channel-major / frequency-minor (tensorBase.py:11-17)."""
+    bands = torch.pow(2.0, torch.arange(freqs, device=positions.device, dtype=torch.float32))
+    scaled = (positions.unsqueeze(-1) * bands).flatten(-2)
+    return torch.cat((scaled.sin(), scaled.cos()), dim=-1)
+
+
+def raw2alpha(sigma, dist):
+    """alpha, weights and background transmittance of one ray batch (tensorBase.py:19-26).
+    Exported because renderer.py imports it; the fused kernel implements the same recurrence
+    with a warp-shuffle scan."""
+    alpha = 1. - torch.exp(-sigma * dist)
+    keep = torch.cat((torch.ones_like(alpha[:, :1]), 1. - alpha + 1e-10), dim=-1)
+    trans = torch.cumprod(keep, dim=-1)
+    return alpha, alpha * trans[:, :-1], trans[:, -1:]
+
+
+def SHRender(xyz_sampled, viewdirs, features):
+    basis = eval_sh_bases(2, viewdirs).unsqueeze(1)
+    coeff = features.reshape(-1, 3, basis.shape[-1])
+    return torch.relu((basis * coeff).sum(-1) + 0.5)
+
+
+def RGBRender(xyz_sampled, viewdirs, features):
+    return features
+
+
+class AlphaGridMask(torch.nn.Module):
+    """Binary occupancy volume with its own box (tensorBase.py:41-59)."""
+
+    def __init__(self, device, aabb, alpha_volume):
+        super().__init__()
+        self.device = device
+        self.aabb = aabb.to(self.device)
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invgridSize = 1.0 / self.aabbSize * 2
+        self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
+        self.gridSize = torch.LongTensor(
+            [alpha_volume.shape[-1], alpha_volume.shape[-2], alpha_volume.shape[-3]]).to(self.device)
+
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invgridSize - 1
+
+    def sample_alpha(self, xyz_sampled):
+        grid = self.normalize_coord(xyz_sampled).view(1, -1, 1, 1, 3)
+        return F.grid_sample(self.alpha_volume, grid, align_corners=True).view(-1)
+
+    def native(self) -> nat.T2NAlphaMask:
+        vol = self.alpha_volume
+        if vol.dtype != torch.float32 or not vol.is_contiguous():
+            vol = vol.float().contiguous()
+            self.alpha_volume = vol
+        m = nat.T2NAlphaMask()
+        m.volume = vol.data_ptr()
+        m.dims = nat.I3(vol.shape[-1], vol.shape[-2], vol.shape[-3])
+        m.aabb_lo = nat.F3(*self.aabb[0].tolist())
+        m.inv_size = nat.F3(*self.invgridSize.tolist())
+        return m
+
+
+# ------------------------------------------------------------------------------------------------
+# shading heads: parameter containers with the reference's state-dict keys.  Their arithmetic
+# runs inside the fused appearance kernel; calling them directly evaluates the same formula with
+# torch ops on whatever device the inputs live on (used by tests, never by TensorBase.forward).
+# ------------------------------------------------------------------------------------------------
+class _MLPHead(torch.nn.Module):
+    def _build(self, in_dim, featureC):
+        self.in_mlpC = in_dim
+        l1 = torch.nn.Linear(in_dim, featureC)
+        l2 = torch.nn.Linear(featureC, featureC)
+        l3 = torch.nn.Linear(featureC, 3)
+        self.mlp = torch.nn.Sequential(l1, torch.nn.ReLU(inplace=True), l2, torch.nn.ReLU(inplace=True), l3)
+        torch.nn.init.constant_(self.mlp[-1].bias, 0)
+
+    def _run(self, cols):
+        return torch.sigmoid(self.mlp(torch.cat(cols, dim=-1)))
+
+
+class MLPRender_Fea(_MLPHead):                       # tensorBase.py:62-86
+    def __init__(self, inChanel, viewpe=6, feape=6, featureC=128):
+        super().__init__()
+        self.viewpe, self.feape = viewpe, feape
+        self._build(2 * viewpe * 3 + 2 * feape * inChanel + 3 + inChanel, featureC)
+
+    def forward(self, pts, viewdirs, features):
+        cols = [features, viewdirs]
+        if self.feape > 0:
+            cols.append(positional_encoding(features, self.feape))
+        if self.viewpe > 0:
+            cols.append(positional_encoding(viewdirs, self.viewpe))
+        return self._run(cols)
+
+
+class MLPRender_Fea_noview(_MLPHead):                # tensorBase.py:88-109
+    def __init__(self, inChanel, feape=6, featureC=128):
+        super().__init__()
+        self.feape = feape
+        self._build(2 * feape * inChanel + inChanel, featureC)
+
+    def forward(self, pts, viewdirs, features):
+        cols = [features]
+        if self.feape > 0:
+            cols.append(positional_encoding(features, self.feape))
+        return self._run(cols)
+
+
+class MLPRender_PE(_MLPHead):                        # tensorBase.py:111-135
+    """Kept for constructor parity.  In the reference this head cannot run: its first layer is
+    sized for 3 extra `pts` columns that forward never concatenates (tensorBase.py:115 vs
+    :124-130), so any render raises a shape error.  TensorBase.forward raises the same way."""
+
+    def __init__(self, inChanel, viewpe=6, pospe=6, featureC=128):
+        super().__init__()
+        self.viewpe, self.pospe = viewpe, pospe
+        self._build((3 + 2 * viewpe * 3) + (3 + 2 * pospe * 3) + inChanel, featureC)
+
+    def forward(self, pts, viewdirs, features):
+        cols = [features, viewdirs]
+        if self.pospe > 0:
+            cols.append(positional_encoding(pts, self.pospe))
+        if self.viewpe > 0:
+            cols.append(positional_encoding(viewdirs, self.viewpe))
+        return self._run(cols)
+
+
+class MLPRender(_MLPHead):                           # tensorBase.py:137-159
+    def __init__(self, inChanel, viewpe=6, featureC=128):
+        super().__init__()
+        self.viewpe = viewpe
+        self._build((3 + 2 * viewpe * 3) + inChanel, featureC)
+
+    def forward(self, pts, viewdirs, features):
+        cols = [features, viewdirs]
+        if self.viewpe > 0:
+            cols.append(positional_encoding(viewdirs, self.viewpe))
+        return self._run(cols)
+
+
+def decoder_recipe(mode: str, app_dim: int, fea_pe: int, view_pe: int):
+    """Column recipe the kernels use to build the decoder input on the fly.
+
+    Base vector per sample: [feature(app_dim) | viewdir(3) | unit-cube xyz(3) | 0].  Internal
+    columns come in pairs (2q, 2q+1): either two identity columns or (sin, cos) of one base
+    entry times 2**f.  Returns (mlp_in, col_perm[Kp], pair_desc[Kp/2]) where col_perm maps an
+    internal column to the reference's column of mlp[0].weight (-1 = zero padding)."""
+    A = app_dim
+    view0, zero = A, A + 6
+    ident: List[tuple] = [(c, c) for c in range(A)]            # (base index, reference column)
+    trig: List[tuple] = []                                     # (base index, f, sin col, cos col)
+    col = A
+    if mode in ("MLP_Fea", "MLP"):
+        ident += [(view0 + j, col + j) for j in range(3)]
+        col += 3
+    if mode in ("MLP_Fea_noview", "MLP_Fea") and fea_pe > 0:
+        n = A * fea_pe
+        trig += [(c, f, col + c * fea_pe + f, col + n + c * fea_pe + f) for c in range(A) for f in range(fea_pe)]
+        col += 2 * n
+    if mode in ("MLP_Fea", "MLP") and view_pe > 0:
+        n = 3 * view_pe
+        trig += [(view0 + j, f, col + j * view_pe + f, col + n + j * view_pe + f)
+                 for j in range(3) for f in range(view_pe)]
+        col += 2 * n
+    mlp_in = col
+    perm: List[int] = []
+    pairs: List[int] = []
+    for q in range(0, len(ident), 2):
+        a = ident[q]
+        b = ident[q + 1] if q + 1 < len(ident) else (zero, -1)
+        pairs.append(a[0] | (b[0] << 8))
+        perm += [a[1], b[1]]
+    for (src, f, cs, cc) in trig:
+        pairs.append(src | (zero << 8) | (f << 16) | (1 << 20))
+        perm += [cs, cc]
+    while len(perm) % 32:
+        pairs.append(zero | (zero << 8))
+        perm += [-1, -1]
+    return mlp_in, perm, pairs
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd bridge
+# ------------------------------------------------------------------------------------------------
+def _texel_major(t: torch.Tensor) -> torch.Tensor:
+    """[1,C,H,W] tensor whose memory is [H][W][C] (what the C ABI takes)."""
+    return t if t.is_contiguous(memory_format=_CL) else t.contiguous(memory_format=_CL)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class _RenderFn(torch.autograd.Function):
+    """rgb_map, depth_map, z_vals, weight = render(rays; parameters)  via t2n_render_forward /
+    t2n_render_backward."""
+
+    @staticmethod
+    def forward(ctx, model, rays, jitter, n_samples, is_train, white_bg, *params):
+        lib = nat.load()
+        dev = rays.device
+        R, S = rays.shape[0], n_samples
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        p_cl = model._native_param_tensors(params)
+        field = model._native_field()
+        pstruct = model._native_params(p_cl)
+        f32 = dict(device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+        rgb_map = torch.empty((R, 3), **f32)
+        depth_map = torch.empty((R,), **f32)
+        z_vals = torch.empty((R, S), **f32)
+        weight = torch.empty((R, S), **f32)
+        sc = dict(
+            sigma_feat=torch.empty((R, S), **f32) if need_bwd else None,
+            trans=torch.empty((R, S), **f32) if need_bwd else None,
+            acc=torch.empty((R,), **f32), dsum=torch.empty((R,), **f32),
+            ray_start=torch.empty((R,), **i32), ray_count=torch.empty((R,), **i32),
+            slots=torch.empty((R * S,), **i32), app_rgb=torch.empty((R * S, 3), **f32),
+            counters=torch.empty((8,), **i32),
+            w1_packed=model._w1_packed_buffer(dev),
+            ray_flags=torch.empty((R,), **i32),
+            w1_grad_packed=None)
+        mask = model.alphaMask.native() if model.alphaMask is not None else None
+        batch = nat.T2NBatch(_ptr(rays), _ptr(jitter), R, S, int(is_train), int(white_bg))
+        outs = nat.T2NOutputs(_ptr(rgb_map), _ptr(depth_map), _ptr(z_vals), _ptr(weight))
+        scratch = nat.T2NScratch(*[_ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.t2n_render_forward(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
+                                        C.byref(batch), C.byref(outs), C.byref(scratch), stream)
+        nat.check(rc, "t2n_render_forward")
+        model._last_counters = sc["counters"]
+        if need_bwd:
+            ctx.model = model
+            ctx.args = (R, S, bool(is_train), bool(white_bg))
+            ctx.scratch = sc
+            ctx.n_params = len(params)
+            ctx.save_for_backward(rays, jitter if jitter is not None else rays.new_empty(0), z_vals, weight, rgb_map, *p_cl)
+        ctx.mark_non_differentiable(z_vals)
+        return rgb_map, depth_map, z_vals, weight
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_z, g_w):
+        lib = nat.load()
+        model = ctx.model
+        R, S, is_train, white_bg = ctx.args
+        rays, jitter, z_vals, weight, rgb_map, *p_cl = ctx.saved_tensors
+        dev = rays.device
+        sc = ctx.scratch
+        field = model._native_field()
+        pstruct = model._native_params(p_cl)
+        g_rgb = (g_rgb if g_rgb is not None else torch.zeros_like(rgb_map)).contiguous().float()
+        g_depth = (g_depth if g_depth is not None else torch.zeros((R,), device=dev)).contiguous().float()
+        g_w = None if g_w is None else g_w.contiguous().float()
+        grads = model._grad_buffers(p_cl)
+        gstruct = model._native_grads(grads)
+        if model._is_mlp:
+            sc["w1_grad_packed"] = torch.empty_like(sc["w1_packed"])
+        mask = model.alphaMask.native() if model.alphaMask is not None else None
+        batch = nat.T2NBatch(_ptr(rays), _ptr(jitter) if jitter.numel() else None, R, S, int(is_train), int(white_bg))
+        outs = nat.T2NOutputs(_ptr(rgb_map), None, _ptr(z_vals), _ptr(weight))
+        scratch = nat.T2NScratch(*[_ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.t2n_render_backward(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
+                                         C.byref(batch), C.byref(outs), C.byref(scratch), _ptr(g_rgb), _ptr(g_depth),
+                                         _ptr(g_w), C.byref(gstruct), stream)
+        nat.check(rc, "t2n_render_backward")
+        ctx.scratch = None
+        return (None, None, None, None, None, None, *model._grads_for_autograd(grads))
+
+
+# ------------------------------------------------------------------------------------------------
+# TensorBase
+# ------------------------------------------------------------------------------------------------
+class TensorBase(torch.nn.Module):
+    def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
+                 shadingMode='MLP_PE', alphaMask=None, near_far=[2.0, 6.0],
+                 density_shift=-10, alphaMask_thres=0.001, distance_scale=25, rayMarch_weight_thres=0.0001,
+                 pos_pe=6, view_pe=6, fea_pe=6, featureC=128, step_ratio=2.0,
+                 fea2denseAct='softplus'):
+        super().__init__()
+        self.density_n_comp = density_n_comp
+        self.app_n_comp = appearance_n_comp
+        self.app_dim = app_dim
+        self.aabb = aabb
+        self.alphaMask = alphaMask
+        self.device = device
+
+        self.density_shift = density_shift
+        self.alphaMask_thres = alphaMask_thres
+        self.distance_scale = distance_scale
+        self.rayMarch_weight_thres = rayMarch_weight_thres
+        self.fea2denseAct = fea2denseAct
+        self.near_far = near_far
+        self.step_ratio = step_ratio
+
+        self.update_stepSize(gridSize)
+
+        self.matMode = [[0, 1], [0, 2], [1, 2]]
+        self.vecMode = [2, 1, 0]
+        self.comp_w = [1, 1, 1]
+
+        self.init_svd_volume(gridSize[0], device)
+
+        self.shadingMode, self.pos_pe, self.view_pe, self.fea_pe, self.featureC = \
+            shadingMode, pos_pe, view_pe, fea_pe, featureC
+        self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
+        self._recipe_cache = None
+        self._w1p = None
+        self._last_counters = None
+
+    # ---- construction ------------------------------------------------------------------------
+    def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
+        heads = {
+            'MLP_PE': lambda: MLPRender_PE(self.app_dim, view_pe, pos_pe, featureC).to(device),
+            'MLP_Fea': lambda: MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC).to(device),
+            'MLP_Fea_noview': lambda: MLPRender_Fea_noview(self.app_dim, fea_pe, featureC).to(device),
+            'MLP': lambda: MLPRender(self.app_dim, view_pe, featureC).to(device),
+            'SH': lambda: SHRender,
+            'RGB': lambda: RGBRender,
+        }
+        if shadingMode not in heads:
+            print("Unrecognized shading module")
+            exit()
+        if shadingMode == 'RGB':
+            assert self.app_dim == 3
+        self.renderModule = heads[shadingMode]()
+        print("pos_pe", pos_pe, "view_pe", view_pe, "fea_pe", fea_pe)
+        print(self.renderModule)
+
+    def update_stepSize(self, gridSize):
+        """units / stepSize / nSamples as tensorBase.py:220-231.  The fp32 tensor arithmetic is
+        evaluated on the host (bit-identical to the reference on CPU; the 3-element mean is the only
+        op whose order a device could change) and the results are moved to the module's device."""
+        print("aabb", self.aabb.view(-1))
+        print("grid size", gridSize)
+        aabb = self.aabb.detach().float().cpu()
+        size = aabb[1] - aabb[0]
+        grid = torch.LongTensor([int(g) for g in gridSize])
+        units = size / (grid - 1)
+        step = torch.mean(units) * self.step_ratio
+        diag = torch.sqrt(torch.sum(torch.square(size)))
+        self.aabbSize = size.to(self.device)
+        self.invaabbSize = (2.0 / size).to(self.device)
+        self.gridSize = grid.to(self.device)
+        self.units = units.to(self.device)
+        self.stepSize = step.to(self.device)
+        self.aabbDiag = diag.to(self.device)
+        self.nSamples = int((diag / step).item()) + 1
+        self._field_cache = None
+        print("sampling step size: ", self.stepSize)
+        print("sampling number: ", self.nSamples)
+
+    def init_svd_volume(self, res, device):
+        pass
+
+    def compute_features(self, xyz_sampled):
+        pass
+
+    def compute_densityfeature(self, xyz_sampled):
+        pass
+
+    def compute_appfeature(self, xyz_sampled):
+        pass
+
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invaabbSize - 1
+
+    def get_optparam_groups(self, lr_init_spatial=0.02, lr_init_network=0.001):
+        pass
+
+    # ---- checkpointing (tensorBase.py:251-290) -------------------------------------------------
+    def get_kwargs(self):
+        return {
+            'aabb': self.aabb,
+            'gridSize': self.gridSize.tolist(),
+            'density_n_comp': self.density_n_comp,
+            'appearance_n_comp': self.app_n_comp,
+            'app_dim': self.app_dim,
+            'density_shift': self.density_shift,
+            'alphaMask_thres': self.alphaMask_thres,
+            'distance_scale': self.distance_scale,
+            'rayMarch_weight_thres': self.rayMarch_weight_thres,
+            'fea2denseAct': self.fea2denseAct,
+            'near_far': self.near_far,
+            'step_ratio': self.step_ratio,
+            'shadingMode': self.shadingMode,
+            'pos_pe': self.pos_pe,
+            'view_pe': self.view_pe,
+            'fea_pe': self.fea_pe,
+            'featureC': self.featureC,
+        }
+
+    def save(self, path):
+        ckpt = {'kwargs': self.get_kwargs(), 'state_dict': self.state_dict()}
+        if self.alphaMask is not None:
+            occ = self.alphaMask.alpha_volume.bool().cpu().numpy()
+            ckpt['alphaMask.shape'] = occ.shape
+            ckpt['alphaMask.mask'] = np.packbits(occ.reshape(-1))
+            ckpt['alphaMask.aabb'] = self.alphaMask.aabb.cpu()
+        torch.save(ckpt, path)
+
+    def load(self, ckpt):
+        if 'alphaMask.aabb' in ckpt.keys():
+            n = int(np.prod(ckpt['alphaMask.shape']))
+            bits = np.unpackbits(ckpt['alphaMask.mask'])[:n].reshape(ckpt['alphaMask.shape'])
+            self.alphaMask = AlphaGridMask(self.device, ckpt['alphaMask.aabb'].to(self.device),
+                                           torch.from_numpy(bits).float().to(self.device))
+        self.load_state_dict(ckpt['state_dict'])
+
+    # ---- samplers kept for API parity (the fused kernel does this work on the hot path) ---------
+    def sample_ray_ndc(self, rays_o, rays_d, is_train=True, N_samples=-1):
+        raise NotImplementedError("ndc_ray=1 is outside the Text2NeRF flow (SURVEY.md 8b); not built")
+
+    def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1):
+        """Sample positions with torch ops (tensorBase.py:304-323).  Only used by
+        filtering_rays(bbox_only=False); TensorBase.forward samples inside the kernel."""
+        N_samples = N_samples if N_samples > 0 else self.nSamples
+        near, far = self.near_far
+        safe_d = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+        t_hi = (self.aabb[1] - rays_o) / safe_d
+        t_lo = (self.aabb[0] - rays_o) / safe_d
+        t_min = torch.minimum(t_hi, t_lo).amax(-1).clamp(min=near, max=far)
+        idx = torch.arange(N_samples)[None].float()
+        if is_train:
+            idx = idx.repeat(rays_d.shape[-2], 1)
+            idx += torch.rand_like(idx[:, [0]])
+        z = t_min[..., None] + self.stepSize * idx.to(rays_o.device)
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., None]
+        outside = ((self.aabb[0] > pts) | (pts > self.aabb[1])).any(dim=-1)
+        return pts, z, ~outside
+
+    def shrink(self, new_aabb, voxel_size):
+        pass
+
+    # ---- alpha-mask maintenance (tensorBase.py:328-404) ----------------------------------------
+    @torch.no_grad()
+    def getDenseAlpha(self, gridSize=None):
+        gridSize = self.gridSize if gridSize is None else gridSize
+        gx, gy, gz = [int(g) for g in gridSize]
+        lin = [torch.linspace(0, 1, g) for g in (gx, gy, gz)]
+        samples = torch.stack(torch.meshgrid(*lin, indexing="ij"), -1).to(self.device)
+        dense_xyz = self.aabb[0] * (1 - samples) + self.aabb[1] * samples
+        alpha = self.compute_alpha(dense_xyz.view(-1, 3), self.stepSize).view(gx, gy, gz)
+        return alpha, dense_xyz
+
+    @torch.no_grad()
+    def updateAlphaMask(self, gridSize=(200, 200, 200)):
+        alpha, dense_xyz = self.getDenseAlpha(gridSize)
+        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
+        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        total_voxels = gridSize[0] * gridSize[1] * gridSize[2]
+        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gridSize[::-1])
+        alpha = (alpha >= self.alphaMask_thres).float()
+        self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
+        occupied = dense_xyz[alpha > 0.5]
+        xyz_min, xyz_max = occupied.amin(0), occupied.amax(0)
+        print(f"bbox: {xyz_min, xyz_max} alpha rest %%%f" % (torch.sum(alpha) / total_voxels * 100))
+        return torch.stack((xyz_min, xyz_max))
+
+    @torch.no_grad()
+    def filtering_rays(self, all_rays, all_rgbs, all_depth=None, N_samples=256, chunk=10240 * 5, bbox_only=False):
+        print('========> filtering rays ...')
+        tt = time.time()
+        N = torch.tensor(all_rays.shape[:-1]).prod()
+        keep = []
+        for idx in torch.split(torch.arange(N), chunk):
+            rays = all_rays[idx].to(self.device)
+            o, d = rays[..., :3], rays[..., 3:6]
+            if bbox_only:
+                safe_d = torch.where(d == 0, torch.full_like(d, 1e-6), d)
+                t_hi = (self.aabb[1] - o) / safe_d
+                t_lo = (self.aabb[0] - o) / safe_d
+                hit = torch.maximum(t_hi, t_lo).amin(-1) > torch.minimum(t_hi, t_lo).amax(-1)
+            else:
+                pts, _, _ = self.sample_ray(o, d, N_samples=N_samples, is_train=False)
+                hit = (self.alphaMask.sample_alpha(pts).view(pts.shape[:-1]) > 0).any(-1)
+            keep.append(hit.cpu())
+        keep = torch.cat(keep).view(all_rgbs.shape[:-1])
+        print(f'Ray filtering done! takes {time.time()-tt} s. ray mask ratio: {torch.sum(keep) / N}')
+        if all_depth is not None:
+            return all_rays[keep], all_rgbs[keep], all_depth[keep]
+        return all_rays[keep], all_rgbs[keep]
+
+    def feature2density(self, density_features):
+        if self.fea2denseAct == "softplus":
+            return F.softplus(density_features + self.density_shift)
+        elif self.fea2denseAct == "relu":
+            return F.relu(density_features)
+
+    def compute_alpha(self, xyz_locs, length=1):
+        """1 - exp(-sigma(x) * length) at arbitrary points (tensorBase.py:413-433), one kernel."""
+        lib = nat.load()
+        xyz = xyz_locs.reshape(-1, 3).contiguous().float()
+        out = torch.empty((xyz.shape[0],), device=xyz.device, dtype=torch.float32)
+        if xyz.shape[0] == 0:
+            return out.view(xyz_locs.shape[:-1])
+        params = self._flat_params()
+        p_cl = self._native_param_tensors(params)
+        field, pstruct = self._native_field(), self._native_params(p_cl)
+        mask = self.alphaMask.native() if self.alphaMask is not None else None
+        with torch.cuda.device(xyz.device):
+            rc = lib.t2n_compute_alpha(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
+                                       xyz.data_ptr(), xyz.shape[0], float(length), out.data_ptr(),
+                                       torch.cuda.current_stream(xyz.device).cuda_stream)
+        nat.check(rc, "t2n_compute_alpha")
+        return out.view(xyz_locs.shape[:-1])
+
+    # ---- the hot path ------------------------------------------------------------------------------
+    def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1):
+        """Same contract as tensorBase.py:436-507: returns rgb_map[R,3], depth_map[R],
+        z_vals[R,S], weight[R,S]; differentiable w.r.t. every parameter through rgb_map,
+        depth_map and weight."""
+        if ndc_ray:
+            raise NotImplementedError("ndc_ray=1 is outside the Text2NeRF flow (SURVEY.md 8b); not built")
+        if self.shadingMode == 'MLP_PE':
+            k = self.renderModule.in_mlpC
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied (Nx{k - 3} and {k}x{self.featureC}): "
+                               "MLP_PE is not runnable in the reference either (tensorBase.py:115 vs :124-130)")
+        if not rays_chunk.is_cuda:
+            raise nat.NativeLibraryError("text2nerf_b200 renders on a CUDA device only; rays are on " + str(rays_chunk.device))
+        rays = rays_chunk.detach()
+        if rays.dtype != torch.float32 or not rays.is_contiguous() or rays.shape[-1] != 6:
+            rays = rays[..., :6].float().contiguous() if rays.shape[-1] >= 6 else rays
+        if rays.dim() != 2 or rays.shape[-1] != 6:
+            raise ValueError("rays_chunk must be [R,6+] (origin, direction)")
+        R = rays.shape[0]
+        S = int(N_samples) if N_samples > 0 else self.nSamples
+        jitter = None
+        if is_train:
+            # one U[0,1) per ray from the CPU generator, as tensorBase.py:313-317 draws it
+            jitter = torch.rand(R, 1).to(rays.device, non_blocking=True).view(-1)
+        # tensorBase.py:497 -- the extra CPU draw happens only when white_bg is False
+        white = bool(white_bg) or (bool(is_train) and bool(torch.rand((1,)) < 0.5))
+        params = self._flat_params()
+        max_rays = max(1, ((1 << 31) - 1) // S)
+        if R <= max_rays:
+            return _RenderFn.apply(self, rays, jitter, S, bool(is_train), white, *params)
+        outs = [[], [], [], []]
+        for s in range(0, R, max_rays):
+            part = _RenderFn.apply(self, rays[s:s + max_rays].contiguous(),
+                                   None if jitter is None else jitter[s:s + max_rays].contiguous(),
+                                   S, bool(is_train), white, *params)
+            for lst, t in zip(outs, part):
+                lst.append(t)
+        return tuple(torch.cat(x) for x in outs)
+
+    # ---- native glue (overridden / completed by TensorVMSplit) ------------------------------------
+    @property
+    def _is_mlp(self):
+        return isinstance(self.renderModule, torch.nn.Module)
+
+    def _native_field(self) -> nat.T2NField:
+        if self._field_cache is not None and self._field_cache[0] == self.shadingMode:
+            return self._field_cache[1]
+        f = nat.T2NField()
+        f.aabb_lo = nat.F3(*self.aabb[0].tolist())
+        f.aabb_hi = nat.F3(*self.aabb[1].tolist())
+        f.inv_aabb = nat.F3(*self.invaabbSize.tolist())
+        f.grid = nat.I3(*self.gridSize.tolist())
+        f.step_size = float(self.stepSize.item())
+        f.near_clip, f.far_clip = float(self.near_far[0]), float(self.near_far[1])
+        f.distance_scale = float(self.distance_scale)
+        f.density_shift = float(self.density_shift)
+        f.weight_thres = float(self.rayMarch_weight_thres)
+        f.eval_z_min = 2.0
+        f.act = {"softplus": 0, "relu": 1}[self.fea2denseAct]
+        f.shading = SHADE_IDS[self.shadingMode]
+        f.app_dim = int(self.app_dim)
+        f.feature_c = int(self.featureC)
+        f.n_sigma = nat.I3(*[int(c) for c in self.density_n_comp])
+        f.n_app = nat.I3(*[int(c) for c in self.app_n_comp])
+        if self._is_mlp:
+            mlp_in, perm, _ = self._recipe()
+            f.mlp_in, f.mlp_in_pad = mlp_in, len(perm)
+        else:
+            f.mlp_in, f.mlp_in_pad = 0, 32
+        self._field_cache = (self.shadingMode, f)
+        return f
+
+    def _recipe(self):
+        key = (self.shadingMode, self.app_dim, self.fea_pe, self.view_pe)
+        if self._recipe_cache is None or self._recipe_cache[0] != key:
+            mlp_in, perm, pairs = decoder_recipe(self.shadingMode, self.app_dim, self.fea_pe, self.view_pe)
+            assert mlp_in == self.renderModule.in_mlpC, (mlp_in, self.renderModule.in_mlpC)
+            self._recipe_cache = (key, (mlp_in, perm, pairs), {})
+        return self._recipe_cache[1]
+
+    def _recipe_tensors(self, device):
+        self._recipe()
+        cache = self._recipe_cache[2]
+        if device not in cache:
+            _, perm, pairs = self._recipe_cache[1]
+            cache[device] = (torch.tensor(perm, dtype=torch.int32, device=device),
+                             torch.tensor(pairs, dtype=torch.int32, device=device))
+        return cache[device]
+
+    def _w1_packed_buffer(self, device):
+        if not self._is_mlp:
+            return None
+        n = self.featureC * len(self._recipe()[1])
+        if self._w1p is None or self._w1p.device != device or self._w1p.numel() != n:
+            self._w1p = torch.empty((n,), device=device, dtype=torch.float32)
+        return self._w1p
