@@ -32,7 +32,9 @@ def _check_forward(out, ref, thres_note=""):
     assert float((w - ref["weight"]).abs().max()) <= 2e-6, thres_note
     big = ref["weight"] > 1e-3
     if big.any():
-        assert rel_err(w[big], ref["weight"][big]) <= 2e-5
+        # exp(-sigma*dist*25) turns the ~3e-6 absolute noise of the density feature sum into a
+        # relative error of that size times the optical depth; 1e-4 is the RGB gate
+        assert rel_err(w[big], ref["weight"][big]) <= 1e-4
     # rgb in [0,1]: relative error with a floor of 0.05 (values that small are dominated by absolute error)
     assert rel_err(rgb, ref["rgb_map"], floor=0.05) <= RGB_RTOL, thres_note
     assert rel_err(depth, ref["depth_map"], floor=0.05) <= RGB_RTOL

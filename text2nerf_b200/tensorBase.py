@@ -232,7 +232,7 @@ class _RenderFn(torch.autograd.Function):
         lib = nat.load()
         dev = rays.device
         R, S = rays.shape[0], n_samples
-        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_bwd = any(ctx.needs_input_grad[6:])      # grad mode is off inside Function.forward
         p_cl = model._native_param_tensors(params)
         field = model._native_field()
         pstruct = model._native_params(p_cl)
