@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the TensoRF ray-marching hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: launched by torch.distributed.run, one rank per GPU)
+
+Workload (BASELINE.json configs[1], "lego 800x800"): TensorVMSplit 300^3 (16/48 components,
+MLP_Fea_noview 351->128->128->3), box +-1.5 pushed to z in [2.5, 5.5] (the reference's eval path
+drops world z <= 2, tensorBase.py:459-462), step_ratio 0.5 -> 1036 samples per ray, one 800x800
+pin-hole view = 640,000 rays per step, synthetic "fog" field (seeded init, density factors x10.8,
+SURVEY.md 8d).  Data is synthetic and weights are random: no datasets exist offline.
+
+One step = one full-view forward render (eval, no_grad) through the fused kernels.
+  value      Mrays/s of that step with rays already resident in HBM (whole job, all ranks)
+  e2e        the same view through the reference-facing API OctreeRender_trilinear_fast with the
+             rays in pinned HOST memory (H2D inside the timed region) and rgb/depth maps read
+             back to the host (D2H), as renderer.evaluation does per view (renderer.py:89-93)
+  fwd_bwd    second timed region: forward+backward of the Text2NeRF data loss
+             (text2nerf_main.py:563-575) on 4096-ray training batches; with N > 1 ranks every step
+             ends with ONE NCCL all-reduce of the flat gradient buffer
+  roofline   dominant kernel of the forward: algorithmic bytes / CUDA-event time
+  cpu_baseline  the oracle (CPU port of the reference, same ATen ops) on a bounded ray sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H = W = 800
+FOCAL = 1111.1
+GRID = [300, 300, 300]
+AABB = [[-1.5, -1.5, 2.5], [1.5, 1.5, 5.5]]
+NEAR_FAR = [2.0, 6.0]
+STEP_RATIO = 0.5
+TRAIN_BATCH = 4096
+TRAIN_BATCHES_PER_STEP = 8
+CPU_RAYS_FWD = 2048
+CPU_RAYS_BWD = 512
+METRIC = "Mrays/s forward (eval) full-view render at 800x800, lego-shaped TensorVMSplit 300^3"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    return ap.parse_args()
+
+
+def make_spec():
+    from oracle import t2n_oracle as orc       # spec/param generator only; never on the timed product path
+    return orc.FieldSpec(aabb=AABB, grid=GRID, near_far=NEAR_FAR, step_ratio=STEP_RATIO)
+
+
+def make_params(spec):
+    from oracle import t2n_oracle as orc
+    return orc.init_params(spec, seed=0, density_gain=10.8, app_gain=1.0)
+
+
+def view_pose(rank):
+    """Camera at the origin looking down +z, yawed a little per rank so ranks render different views."""
+    import math
+    a = 0.04 * rank
+    return torch.tensor([[math.cos(a), 0.0, math.sin(a), 0.0],
+                         [0.0, 1.0, 0.0, 0.0],
+                         [-math.sin(a), 0.0, math.cos(a), 0.0]], dtype=torch.float32)
+
+
+def host_rays(rank):
+    from oracle import t2n_oracle as orc
+    d = orc.pixel_directions(H, W, [FOCAL, FOCAL])
+    d = d / torch.norm(d, dim=-1, keepdim=True)
+    ro, rd = orc.camera_rays(d, view_pose(rank))
+    return torch.cat([ro, rd], -1).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(spec, params, rays_cpu, steps, warmup, what):
+    """Times the oracle on the host cores: bounded ray sample of the same workload."""
+    from oracle import t2n_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    S = orc.derive_step(spec)[1]
+    g = torch.Generator().manual_seed(0)
+    n = CPU_RAYS_FWD if what == "fwd" else CPU_RAYS_BWD
+    idx = torch.randperm(rays_cpu.shape[0], generator=g)[:n]
+    rays = rays_cpu[idx].contiguous()
+    times = []
+    if what == "fwd":
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                orc.render(spec, params, rays, S, False, True, None)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        jitter = torch.rand(n, 1, generator=g)
+        rgb_gt, depth_gt = torch.rand(n, 3, generator=g), 2 + 4 * torch.rand(n, generator=g)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = orc.render(spec, p, rays, S, True, True, jitter)
+            orc.training_loss(*out, rgb_gt, depth_gt).backward()
+            for v in p.values():
+                v.grad = None
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return n, times
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: same
+    ATen ops, tests pin it bit-exact to the unmodified reference) on the box's host cores."""
+    if rank != 0:
+        return
+    spec = make_spec()
+    params = make_params(spec)
+    rays = host_rays(0)
+    n, times = cpu_reference_leg(spec, params, rays, args.steps, max(1, min(args.warmup, 1)), "fwd")
+    total = sum(times)
+    v = n * len(times) / total / 1e6
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "lego800: 300^3 VM field, 800x800 view, S=1036 (bounded CPU sample per step)"},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} random rays of the 800x800 view per step, S=1036, eval forward"},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    from text2nerf_b200 import OctreeRender_trilinear_fast, TensorVMSplit, _native as nat
+    from text2nerf_b200 import dist as t2n_dist
+    from text2nerf_b200 import ray_utils
+    from oracle import t2n_oracle as orc      # only: synthetic spec/params, the loss formula, cpu_baseline
+
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nat.load()
+
+    spec = make_spec()
+    params = make_params(spec)
+    S = orc.derive_step(spec)[1]
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = TensorVMSplit(spec.aabb_t().to(dev), GRID, dev, density_n_comp=[16, 16, 16],
+                              appearance_n_comp=[48, 48, 48], app_dim=27, near_far=NEAR_FAR,
+                              shadingMode="MLP_Fea_noview", alphaMask_thres=0.001, density_shift=-10,
+                              distance_scale=25, pos_pe=6, view_pe=2, fea_pe=6, featureC=128,
+                              step_ratio=STEP_RATIO, fea2denseAct="softplus")
+    model.load_state_dict({k: v.to(dev) for k, v in params.items()})
+    assert model.nSamples == S == 1036
+
+    pose = view_pose(rank)
+    rays_dev = ray_utils.camera_rays(pose, H, W, [FOCAL, FOCAL], normalize=True, device=dev)
+    rays_pinned = host_rays(rank).pin_memory()
+    n_rays = H * W
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---------------- forward, rays resident in HBM
+    def fwd_resident():
+        with torch.no_grad():
+            model(rays_dev, is_train=False, white_bg=True, ndc_ray=0, N_samples=S)
+
+    # ---------------- forward, end to end through the reference-facing API
+    host_rgb = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory()
+    host_depth = torch.empty((n_rays,), dtype=torch.float32).pin_memory()
+
+    def fwd_e2e():
+        with torch.no_grad():
+            rgb, _, depth, _, _ = OctreeRender_trilinear_fast(rays_pinned, model, chunk=n_rays, N_samples=S,
+                                                              ndc_ray=0, white_bg=True, is_train=False, device=dev)
+        host_rgb.copy_(rgb, non_blocking=True)
+        host_depth.copy_(depth, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        fwd_resident()
+    with ClockSampler(local_rank) as clk:
+        ms_fwd = timed(fwd_resident, args.steps)
+    value = world * n_rays * args.steps / (ms_fwd * 1e-3) / 1e6
+
+    for _ in range(2):
+        fwd_e2e()
+    ms_e2e = timed(fwd_e2e, args.steps)
+    e2e_value = world * n_rays * args.steps / (ms_e2e * 1e-3) / 1e6
+
+    # ---------------- per-kernel roofline (profiled steps outside the timed region)
+    lib = nat.load()
+    lib.t2n_profile_enable(1)
+    ktimes = {}
+    for _ in range(3):
+        fwd_resident()
+        for name, ms in nat.profile_read():
+            ktimes.setdefault(name, []).append(ms)
+    lib.t2n_profile_enable(0)
+    n_app, n_valid = model.app_sample_count()
+    kbytes = {"march": n_rays * (24 + 8 * S) + n_valid * 1152,
+              "appearance": n_app * (3456 + 4 + 4 + 12),
+              "finalize": n_rays * (8 + 8 + 16) + n_app * (4 + 4 + 12)}
+    kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}
+    dom = max(kavg, key=kavg.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = kbytes[dom] / (kavg[dom] * 1e-3) / 1e9
+    total_bytes = n_rays * (40 + 8 * S) + n_valid * 1152 + n_app * 3456
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "kernel_ms": kavg, "kernel_algorithmic_bytes": kbytes,
+                "path_algorithmic_GBps": total_bytes / (ms_fwd / args.steps * 1e-3) / 1e9,
+                "path_frac": total_bytes / (ms_fwd / args.steps * 1e-3) / 1e9 / peak,
+                "valid_samples_per_ray": n_valid / n_rays, "app_samples_per_ray": n_app / n_rays}
+
+    # ---------------- forward + backward on training batches
+    fwd_bwd = None
+    launches_train = 0
+    if not args.no_train:
+        g = torch.Generator().manual_seed(100 + rank)
+        flat = model.enable_flat_grads(True)
+        batches = []
+        for _ in range(TRAIN_BATCHES_PER_STEP):
+            idx = torch.randint(0, n_rays, (TRAIN_BATCH,), generator=g)
+            batches.append((rays_dev[idx.to(dev)].contiguous(), torch.rand(TRAIN_BATCH, 3, generator=g).to(dev),
+                            (2 + 4 * torch.rand(TRAIN_BATCH, generator=g)).to(dev)))
+        torch.manual_seed(7 + rank)
+
+        def train_step():
+            for rays_b, rgb_gt, depth_gt in batches:
+                flat.zero_()
+                out = model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S)
+                loss = orc.training_loss(*out, rgb_gt, depth_gt)
+                loss.backward()
+                t2n_dist.allreduce_flat_grads(model, world)
+
+        for _ in range(max(args.warmup, 3)):
+            train_step()
+        ms_tr = timed(train_step, args.steps)
+        rays_done = world * TRAIN_BATCH * TRAIN_BATCHES_PER_STEP * args.steps
+        fwd_bwd = {"value": rays_done / (ms_tr * 1e-3) / 1e6, "unit": "Mrays/s", "batch_rays_per_gpu": TRAIN_BATCH,
+                   "ms_per_batch": ms_tr / (args.steps * TRAIN_BATCHES_PER_STEP),
+                   "loss": "rgb MSE + 0.005 depth MSE + 1e3 transmittance (text2nerf_main.py:563-575), no optimiser step",
+                   "collective": "1 NCCL all-reduce of the flat fp32 grad buffer per batch" if world > 1 else "none (1 GPU)"}
+        lib.t2n_profile_enable(1)
+        rays_b, rgb_gt, depth_gt = batches[0]
+        flat.zero_()
+        out = model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S)
+        fk = dict(nat.profile_read())
+        orc.training_loss(*out, rgb_gt, depth_gt).backward()
+        bk = dict(nat.profile_read())
+        lib.t2n_profile_enable(0)
+        fwd_bwd["kernel_ms"] = {**fk, **bk}
+        launches_train = 7 * TRAIN_BATCHES_PER_STEP * args.steps
+        model.enable_flat_grads(False)
+
+    # ---------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n, times = cpu_reference_leg(spec, params, rays_pinned, 2, 1, "fwd")
+        cpu = {"value": n / min(times) / 1e6, "unit": "Mrays/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n} random rays of the same 800x800 view, S=1036, eval forward, best of 2 after 1 warm-up"}
+        if not args.no_train:
+            nb, tb = cpu_reference_leg(spec, params, rays_pinned, 1, 1, "bwd")
+            cpu["fwd_bwd_value"] = nb / min(tb) / 1e6
+            cpu["fwd_bwd_sample"] = f"{nb} rays, S=1036, loss of text2nerf_main.py:563-575 + backward"
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_fwd / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "lego800: TensorVMSplit 300^3 (16/48 comps, MLP_Fea_noview 351-128-128-3), "
+                                       "aabb +-1.5 at z 2.5..5.5, 800x800 view = 640000 rays/step/GPU, S=1036, eval",
+                           "rays_per_step_per_gpu": n_rays, "samples_per_ray": S, "parallelism": f"view-sharded x{world}",
+                           "l2": "per-step working set ~16 GB (outputs [R,S] stream through) >> 126 MB L2; no explicit flush; "
+                                 "the 69 MB of VM factors are L2-resident by design"},
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n_rays * 24,
+                        "d2h_bytes_per_step": n_rays * 16, "ms_per_step": ms_e2e / args.steps,
+                        "api": "text2nerf_b200.OctreeRender_trilinear_fast(pinned host rays) + rgb/depth .cpu()"},
+                "gpu_launches": 4 * args.steps + launches_train,
+                "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "fwd_bwd": fwd_bwd}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

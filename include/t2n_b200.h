@@ -205,6 +205,14 @@ int t2n_rotate_rays(const float* c2w_host, const float* directions, int n, float
 int t2n_compute_alpha(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
                       const float* xyz, int n, float length, float* alpha, t2n_stream_t stream);
 
+/* Measurement aid (bench.py roofline leg; not part of the reference surface).  While enabled,
+ * every forward/backward call records CUDA events on its stream around each kernel it launches.
+ * t2n_profile_read synchronises on the last event and writes up to n (kernel id, milliseconds)
+ * pairs of the most recent call: ids 0=march 1=pack_w1 2=appearance 3=finalize 4=app_backward
+ * 5=unpack_w1_grad 6=ray_backward.  Returns the number of pairs written. */
+int t2n_profile_enable(int on);
+int t2n_profile_read(int* ids, float* ms, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,8 @@ SYMBOLS = {
     "t2n_get_rays": (C.c_int, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "t2n_rotate_rays": (C.c_int, [C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "t2n_profile_enable": (C.c_int, [C.c_int]),
+    "t2n_profile_read": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
     "t2n_compute_alpha": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
                                     C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
 }
@@ -126,6 +128,18 @@ def load(path: Optional[str] = None) -> C.CDLL:
     if path is None:
         _lib = lib
     return lib
+
+
+KERNEL_NAMES = {0: "march", 1: "pack_w1", 2: "appearance", 3: "finalize", 4: "app_backward",
+                5: "unpack_w1_grad", 6: "ray_backward"}
+
+
+def profile_read():
+    """[(kernel name, ms)] of the most recent forward or backward call (profiling enabled)."""
+    ids = (C.c_int * 16)()
+    ms = (C.c_float * 16)()
+    n = load().t2n_profile_read(ids, ms, 16)
+    return [(KERNEL_NAMES.get(ids[i], str(ids[i])), float(ms[i])) for i in range(n)]
 
 
 def check(code: int, what: str) -> None:

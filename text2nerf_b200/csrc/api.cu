@@ -87,6 +87,29 @@ int max_quads(const int n[3]) {
 
 #define T2N_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
+// ---- optional per-kernel event timing (bench.py roofline leg) ----------------------------------
+struct Profiler {
+    bool on = false;
+    static constexpr int kMax = 16;
+    cudaEvent_t ev[2 * kMax] = {};
+    bool created = false;
+    int ids[kMax];
+    int n = 0;
+    void begin_call() { n = 0; }
+    void start(int id, cudaStream_t st) {
+        if (!on || n >= kMax) return;
+        if (!created) { for (auto& e : ev) cudaEventCreate(&e); created = true; }
+        ids[n] = id;
+        cudaEventRecord(ev[2 * n], st);
+    }
+    void stop(cudaStream_t st) {
+        if (!on || n >= kMax) return;
+        cudaEventRecord(ev[2 * n + 1], st);
+        ++n;
+    }
+};
+Profiler g_prof;
+
 AppArgs make_app_args(const T2NField* f, const T2NParams* p, const FieldDev& fd, const T2NBatch* b,
                       const T2NOutputs* out, const T2NScratch* s) {
     AppArgs a;
@@ -128,6 +151,24 @@ const char* t2n_error_string(int code) {
     }
 }
 
+int t2n_profile_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.n = 0;
+    return 0;
+}
+
+int t2n_profile_read(int* ids, float* ms, int n) {
+    if (!ids || !ms || n <= 0) return 0;
+    int k = g_prof.n < n ? g_prof.n : n;
+    for (int i = 0; i < k; ++i) {
+        if (cudaEventSynchronize(g_prof.ev[2 * i + 1]) != cudaSuccess) return i;
+        ids[i] = g_prof.ids[i];
+        ms[i] = 0.f;
+        cudaEventElapsedTime(&ms[i], g_prof.ev[2 * i], g_prof.ev[2 * i + 1]);
+    }
+    return k;
+}
+
 int t2n_device_sm_count(void) {
     DeviceInfo& d = device_info();
     return d.ok ? d.sm_count : 0;
@@ -152,6 +193,7 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
     if (mlp && !scratch->w1_packed) return T2N_E_BADARG;
 
     const FieldDev fd = make_field_dev(field, mask);
+    g_prof.begin_call();
     T2N_CUDA(cudaMemsetAsync(scratch->counters, 0, 8 * sizeof(int32_t), st));
 
     // ---- K1
@@ -177,14 +219,18 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
         int grid = dev.sm_count * ctas_per_sm;
         const int need = (warps_needed + 7) / 8;
         if (grid > need) grid = need;
+        g_prof.start(0, st);
         rc = launch_march(ma, max_quads(field->n_sigma), line_bytes, grid, st);
+        g_prof.stop(st);
         if (rc) return rc;
     }
 
     // ---- K2
     if (mlp) {
+        g_prof.start(1, st);
         rc = launch_pack_w1(params->w1, params->col_perm, field->feature_c, field->mlp_in, field->mlp_in_pad,
                             scratch->w1_packed, st);
+        g_prof.stop(st);
         if (rc) return rc;
     }
     {
@@ -193,7 +239,9 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
         const int smem_bytes = L.total * 4;
         if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
         const int grid = dev.sm_count;
+        g_prof.start(2, st);
         rc = launch_app_forward(aa, max_quads(field->n_app), smem_bytes, grid, st);
+        g_prof.stop(st);
         if (rc) return rc;
     }
 
@@ -203,7 +251,9 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
         fa.rays = batch->rays; fa.weight = out->weight; fa.app_rgb = scratch->app_rgb; fa.slots = scratch->slots;
         fa.ray_start = scratch->ray_start; fa.ray_count = scratch->ray_count; fa.acc = scratch->acc; fa.dsum = scratch->dsum;
         fa.rgb_map = out->rgb_map; fa.depth_map = out->depth_map; fa.ray_flags = scratch->ray_flags; fa.R = batch->R; fa.white_bg = batch->white_bg;
+        g_prof.start(3, st);
         rc = launch_finalize(fa, st);
+        g_prof.stop(st);
         if (rc) return rc;
     }
     return 0;
@@ -244,10 +294,15 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
         const AppBwdSmem BL = app_bwd_smem_layout(b.fw.n_app_total, b.fw.app_dim, b.fw.C, b.fw.Kp);
         const int smem = BL.total * 4;
         if (smem > dev.max_smem_optin) return T2N_E_SHADING;
+        g_prof.begin_call();
+        g_prof.start(4, st);
         rc = launch_app_backward(b, max_quads(field->n_app), smem, dev.sm_count, st);
+        g_prof.stop(st);
         if (rc) return rc;
         if (mlp) {
+            g_prof.start(5, st);
             rc = launch_unpack_w1_grad(scratch->w1_grad_packed, params->col_perm, b.fw.C, field->mlp_in, b.fw.Kp, grads->w1, st);
+            g_prof.stop(st);
             if (rc) return rc;
         }
     }
@@ -274,7 +329,9 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
         int grid = dev.sm_count * ctas_per_sm;
         const int need = (batch->R + 7) / 8;
         if (grid > need) grid = need;
+        g_prof.start(6, st);
         rc = launch_ray_backward(a, max_quads(field->n_sigma), line_bytes, grid, st);
+        g_prof.stop(st);
     }
     return rc;
 }
