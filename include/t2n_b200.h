@@ -32,7 +32,7 @@ extern "C" {
 
 typedef struct CUstream_st* t2n_stream_t;   /* == cudaStream_t */
 
-#define T2N_ABI_VERSION 3
+#define T2N_ABI_VERSION 4
 
 enum {
     T2N_E_BADARG   = -1,   /* null pointer / non-positive size */
@@ -150,6 +150,9 @@ typedef struct T2NOutputs {
  *   ray_flags  R int32                                       bit c set iff rgb_map[.,c] was inside
  *                                                            [0,1] before the clamp (clamp backward)
  *   w1_grad_packed feature_c*mlp_in_pad float (backward only) gradient of w1_packed
+ *   mma_pack   t2n_mma_pack_floats(field) float              pre-swizzled hi/lo TF32 operand images of
+ *                                                            basis_mat, w1 and w2 for the tensor-core
+ *                                                            decoder (NULL selects the FFMA decoder)
  * A batch with R*S >= 2^31 is rejected with T2N_E_CAPACITY. */
 typedef struct T2NScratch {
     float*   sigma_feat;
@@ -164,12 +167,18 @@ typedef struct T2NScratch {
     float*   w1_packed;
     int32_t* ray_flags;
     float*   w1_grad_packed;
+    float*   mma_pack;
 } T2NScratch;
 
 /* ---- entry points ------------------------------------------------------------------------ */
 
 int         t2n_abi_version(void);
 const char* t2n_error_string(int code);
+
+/* Floats the tensor-core decoder needs in T2NScratch.mma_pack for this field, or 0 when the field
+ * is outside its shape envelope (MLP heads, feature_c == 128, app_dim <= 32, every n_app a multiple
+ * of 16, sum(n_app) <= 160) -- then the exact FFMA decoder is the only path. */
+size_t t2n_mma_pack_floats(const T2NField* field);
 
 /* Number of SMs / device check for the current device (0 on failure). */
 int t2n_device_sm_count(void);

@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libt2n_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class NativeLibraryError(RuntimeError):
@@ -75,7 +75,8 @@ class T2NScratch(C.Structure):
     _fields_ = [("sigma_feat", C.c_void_p), ("trans", C.c_void_p), ("acc", C.c_void_p),
                 ("dsum", C.c_void_p), ("ray_start", C.c_void_p), ("ray_count", C.c_void_p),
                 ("slots", C.c_void_p), ("app_rgb", C.c_void_p), ("counters", C.c_void_p),
-                ("w1_packed", C.c_void_p), ("ray_flags", C.c_void_p), ("w1_grad_packed", C.c_void_p)]
+                ("w1_packed", C.c_void_p), ("ray_flags", C.c_void_p), ("w1_grad_packed", C.c_void_p),
+                ("mma_pack", C.c_void_p)]
 
 
 # every symbol include/t2n_b200.h declares, with its ctypes signature
@@ -83,6 +84,7 @@ SYMBOLS = {
     "t2n_abi_version": (C.c_int, []),
     "t2n_error_string": (C.c_char_p, [C.c_int]),
     "t2n_device_sm_count": (C.c_int, []),
+    "t2n_mma_pack_floats": (C.c_size_t, [C.POINTER(T2NField)]),
     "t2n_render_forward": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
                                      C.POINTER(T2NBatch), C.POINTER(T2NOutputs), C.POINTER(T2NScratch),
                                      C.c_void_p]),

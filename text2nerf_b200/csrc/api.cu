@@ -2,6 +2,7 @@
 // Host-side argument checking, launch configuration and kernel dispatch; no allocation, no sync.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "launch.h"
 #include "rays.cuh"
 
@@ -79,6 +80,13 @@ FieldDev make_field_dev(const T2NField* f, const T2NAlphaMask* mask) {
     return d;
 }
 
+bool mma_eligible(const T2NField* f) {
+    if (f->shading > T2N_SHADE_MLP || f->feature_c != 128 || f->app_dim > 32) return false;
+    int tot = 0;
+    for (int i = 0; i < 3; ++i) { if (f->n_app[i] % 16) return false; tot += f->n_app[i]; }
+    return tot <= 160 && f->mlp_in_pad % 32 == 0;
+}
+
 int max_quads(const int n[3]) {
     int m = n[0] > n[1] ? n[0] : n[1];
     m = m > n[2] ? m : n[2];
@@ -149,6 +157,11 @@ const char* t2n_error_string(int code) {
         case T2N_E_DEVICE: return "t2n: current device is not sm_100";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "t2n: unknown error";
     }
+}
+
+size_t t2n_mma_pack_floats(const T2NField* field) {
+    if (!field || !mma_eligible(field)) return 0;
+    return mma_pack_layout(field->n_app[0] + field->n_app[1] + field->n_app[2], field->mlp_in_pad).total;
 }
 
 int t2n_profile_enable(int on) {
@@ -226,23 +239,41 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
     }
 
     // ---- K2
-    if (mlp) {
-        g_prof.start(1, st);
-        rc = launch_pack_w1(params->w1, params->col_perm, field->feature_c, field->mlp_in, field->mlp_in_pad,
-                            scratch->w1_packed, st);
-        g_prof.stop(st);
-        if (rc) return rc;
-    }
     {
         AppArgs aa = make_app_args(field, params, fd, batch, out, scratch);
-        const AppSmem L = app_smem_layout(aa.n_app_total, aa.app_dim, aa.C, aa.Kp);
-        const int smem_bytes = L.total * 4;
-        if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
-        const int grid = dev.sm_count;
-        g_prof.start(2, st);
-        rc = launch_app_forward(aa, max_quads(field->n_app), smem_bytes, grid, st);
-        g_prof.stop(st);
-        if (rc) return rc;
+        const bool use_mma = scratch->mma_pack != nullptr && mma_eligible(field);
+        if (use_mma) {
+            g_prof.start(1, st);
+            rc = launch_pack_mma(aa, params->w1, params->col_perm, field->mlp_in, scratch->mma_pack, st);
+            g_prof.stop(st);
+            if (rc) return rc;
+            AppMmaArgs ma2;
+            ma2.fw = aa;
+            ma2.pack = scratch->mma_pack;
+            const char* tenv = getenv("T2N_MMA_TERMS");          // accuracy study hook; default 3xTF32
+            ma2.terms = tenv ? atoi(tenv) : 7;
+            const int smem_bytes = mma_smem_layout(aa.Kp).total;
+            if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
+            g_prof.start(2, st);
+            rc = launch_app_forward_mma(ma2, smem_bytes, dev.sm_count, st);
+            g_prof.stop(st);
+            if (rc) return rc;
+        } else {
+            if (mlp) {
+                g_prof.start(1, st);
+                rc = launch_pack_w1(params->w1, params->col_perm, field->feature_c, field->mlp_in, field->mlp_in_pad,
+                                    scratch->w1_packed, st);
+                g_prof.stop(st);
+                if (rc) return rc;
+            }
+            const AppSmem L = app_smem_layout(aa.n_app_total, aa.app_dim, aa.C, aa.Kp);
+            const int smem_bytes = L.total * 4;
+            if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
+            g_prof.start(2, st);
+            rc = launch_app_forward(aa, max_quads(field->n_app), smem_bytes, dev.sm_count, st);
+            g_prof.stop(st);
+            if (rc) return rc;
+        }
     }
 
     // ---- K3
@@ -290,6 +321,11 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
                 !grads->w3 || !grads->b3)
                 return T2N_E_BADARG;
             T2N_CUDA(cudaMemsetAsync(scratch->w1_grad_packed, 0, (size_t)b.fw.C * b.fw.Kp * sizeof(float), st));
+            // the backward recomputes the decoder with the exact FFMA tiles: (re)build the packed W1 here so
+            // it does not depend on which decoder the forward used
+            rc = launch_pack_w1(params->w1, params->col_perm, field->feature_c, field->mlp_in, field->mlp_in_pad,
+                                scratch->w1_packed, st);
+            if (rc) return rc;
         }
         const AppBwdSmem BL = app_bwd_smem_layout(b.fw.n_app_total, b.fw.app_dim, b.fw.C, b.fw.Kp);
         const int smem = BL.total * 4;

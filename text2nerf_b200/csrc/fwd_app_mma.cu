@@ -1,0 +1,18 @@
+// tensor-core K2 launchers
+#include "launch.h"
+#include "appearance_mma.cuh"
+namespace t2n {
+int launch_app_forward_mma(const AppMmaArgs& a, int smem_bytes, int grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(app_forward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    app_forward_mma_kernel<<<grid, 256, smem_bytes, st>>>(a);
+    return (int)cudaGetLastError();
+}
+int launch_pack_mma(const AppArgs& a, const float* w1, const int32_t* perm, int K, float* out, cudaStream_t st) {
+    const MmaPack P = mma_pack_layout(a.n_app_total, a.Kp);
+    const int groups = (P.basis_chunks * 32 + P.w1_chunks * 128 + P.w2_chunks * 128) * 8;
+    pack_mma_weights_kernel<<<(groups + 255) / 256, 256, 0, st>>>(a.basis, a.app_dim, a.n_app_total, w1, perm, K, a.Kp,
+                                                               a.w2, out);
+    return (int)cudaGetLastError();
+}
+}  // namespace t2n

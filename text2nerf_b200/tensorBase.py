@@ -14,6 +14,7 @@ module's device, as SURVEY.md section 7 step 2 plans.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from typing import List, Optional, Sequence
 
@@ -251,7 +252,8 @@ class _RenderFn(torch.autograd.Function):
             counters=torch.empty((8,), **i32),
             w1_packed=model._w1_packed_buffer(dev),
             ray_flags=torch.empty((R,), **i32),
-            w1_grad_packed=None)
+            w1_grad_packed=None,
+            mma_pack=model._mma_pack_buffer(dev, field))
         mask = model.alphaMask.native() if model.alphaMask is not None else None
         batch = nat.T2NBatch(_ptr(rays), _ptr(jitter), R, S, int(is_train), int(white_bg))
         outs = nat.T2NOutputs(_ptr(rgb_map), _ptr(depth_map), _ptr(z_vals), _ptr(weight))
@@ -262,6 +264,7 @@ class _RenderFn(torch.autograd.Function):
                                         C.byref(batch), C.byref(outs), C.byref(scratch), stream)
         nat.check(rc, "t2n_render_forward")
         model._last_counters = sc["counters"]
+        model._last_scratch = sc if os.environ.get("T2N_KEEP_SCRATCH") else None
         if need_bwd:
             ctx.model = model
             ctx.args = (R, S, bool(is_train), bool(white_bg))
@@ -627,6 +630,21 @@ class TensorBase(torch.nn.Module):
             cache[device] = (torch.tensor(perm, dtype=torch.int32, device=device),
                              torch.tensor(pairs, dtype=torch.int32, device=device))
         return cache[device]
+
+    def _mma_pack_buffer(self, device, field):
+        """Scratch for the pre-swizzled TF32 operand images of the tensor-core decoder, or None when
+        the field is outside its shape envelope / T2N_DECODER=ffma forces the exact FFMA decoder."""
+        import os
+        if os.environ.get("T2N_DECODER", "mma") == "ffma" or not self._is_mlp:
+            return None
+        n = int(nat.load().t2n_mma_pack_floats(C.byref(field)))
+        if n == 0:
+            return None
+        buf = getattr(self, "_mma_pack", None)
+        if buf is None or buf.device != device or buf.numel() != n:
+            buf = torch.empty((n,), device=device, dtype=torch.float32)
+            self._mma_pack = buf
+        return buf
 
     def _w1_packed_buffer(self, device):
         if not self._is_mlp:
