@@ -196,6 +196,9 @@ def main():
         run_reference_arm(args, rank)
         return
 
+    # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch.distributed as dist
     from text2nerf_b200 import OctreeRender_trilinear_fast, TensorVMSplit, _native as nat
     from text2nerf_b200 import dist as t2n_dist

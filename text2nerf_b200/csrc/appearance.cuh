@@ -157,14 +157,33 @@ __device__ __forceinline__ void load_w_chunk(float* dst, const float* w, int row
     }
 }
 
-// decoder input columns 2q, 2q+1 of one point from its base vector
-__device__ __forceinline__ float2 decoder_pair(int desc, const float* base_row) {
+// Decoder input columns 2q, 2q+1 of one point from its base vector.  sin/cos of base*2^f are
+// produced by ONE precise sincosf of the base angle followed by f angle doublings
+// (sin 2x = 2 s c, cos 2x = 1 - 2 s^2): the recipe lists the frequencies of a channel consecutively, so
+// a thread walking consecutive pairs continues the chain; a chain that starts at f > 0 is rebuilt from
+// f = 0, which makes every value a function of (base, f) only -- identical in every kernel that
+// evaluates the recipe.  Error growth is <= 2^f ulp-level (~3e-6 at f = 5), two orders below the RGB gate.
+struct TrigChain {
+    int src = -1, f = 0;
+    float s = 0.f, c = 1.f;
+};
+__device__ __forceinline__ void trig_double(TrigChain& t) {
+    const float s2 = 2.f * t.s;
+    const float ns = s2 * t.c;
+    t.c = fmaf(-s2, t.s, 1.f);
+    t.s = ns;
+    ++t.f;
+}
+__device__ __forceinline__ float2 decoder_pair(int desc, const float* base_row, TrigChain& t) {
     const int sa = desc & 0xff, sb = (desc >> 8) & 0xff, fq = (desc >> 16) & 0xf;
     if (desc & (1 << 20)) {
-        float v = base_row[sa] * (float)(1 << fq);     // exact power-of-two scaling (tensorBase.py:13-14)
-        float s, c;
-        sincosf(v, &s, &c);
-        return make_float2(s, c);
+        if (!(t.src == sa && t.f < fq)) {
+            sincosf(base_row[sa], &t.s, &t.c);
+            t.src = sa;
+            t.f = 0;
+        }
+        while (t.f < fq) trig_double(t);
+        return make_float2(t.s, t.c);
     }
     return make_float2(base_row[sa], base_row[sb]);
 }
@@ -302,10 +321,11 @@ __global__ void __launch_bounds__(256, 1) app_forward_kernel(const __grid_consta
                 const int m = tid & (kTM - 1), jg = tid / kTM;     // 4 thread groups x 4 pairs = 16 pairs
                 const float* brow = sm + L.base + m * L.base_stride;
                 float* arow = sm + L.a_chunk + m * kChunkStride;
+                TrigChain tc;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int pj = jg * 4 + j;
-                    float2 v = decoder_pair(pairs[kc * (kKC / 2) + pj], brow);
+                    float2 v = decoder_pair(pairs[kc * (kKC / 2) + pj], brow, tc);
                     *reinterpret_cast<float2*>(arow + 2 * pj) = v;
                 }
             }

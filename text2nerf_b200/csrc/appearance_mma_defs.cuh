@@ -18,8 +18,8 @@ struct MmaSmem {        // byte offsets from the 1024-aligned base
     int base;           // float [128][kBaseStride]
     int b1, b2, w3, b3; // floats
     int pairs;          // int32 [Kp/2]
-    int part;           // float [128][2][4] layer-3 partial sums
-    int bars;           // uint64: full[2], free[2], acc
+    int part;           // float [128][4][4] layer-3 partial sums
+    int bars;           // uint64: b_full[2], free[2], acc, a_full[2]
     int tmem_slot;      // uint32
     int total;
 };
@@ -38,7 +38,7 @@ __host__ __device__ inline MmaSmem mma_smem_layout(int Kp) {
     L.b3 = o; o += 16;
     L.pairs = o; o += (Kp / 2) * 4;
     o = (o + 15) & ~15;
-    L.part = o; o += kMmaM * 2 * 4 * 4;
+    L.part = o; o += kMmaM * 4 * 4 * 4;
     L.bars = o; o += 8 * 8;
     L.tmem_slot = o; o += 16;
     L.total = o + 1024;     // slack for the manual 1024-byte alignment of the base

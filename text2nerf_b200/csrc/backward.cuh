@@ -436,10 +436,11 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                     const int m = tid & (kTM - 1), jg = tid / kTM;
                     const float* brow = sm + L.base + m * L.base_stride;
                     float* arow = sm + L.a_chunk + m * kChunkStride;
+                    TrigChain tc;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int pj = jg * 4 + j;
-                        *reinterpret_cast<float2*>(arow + 2 * pj) = decoder_pair(pairs[kc * (kKC / 2) + pj], brow);
+                        *reinterpret_cast<float2*>(arow + 2 * pj) = decoder_pair(pairs[kc * (kKC / 2) + pj], brow, tc);
                     }
                 }
                 cp_async_wait<1>();
@@ -615,10 +616,11 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                         const int m = tid & (kTM - 1), jg = tid / kTM;
                         const float* brow = sm + L.base + m * L.base_stride;
                         float* arow = sm + L.a_chunk + m * kChunkStride;
+                        TrigChain tc;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int pj = jg * 4 + j;
-                            *reinterpret_cast<float2*>(arow + 2 * pj) = decoder_pair(pairs[kc * (kKC / 2) + pj], brow);
+                            *reinterpret_cast<float2*>(arow + 2 * pj) = decoder_pair(pairs[kc * (kKC / 2) + pj], brow, tc);
                         }
                     }
                     cp_async_wait<0>();

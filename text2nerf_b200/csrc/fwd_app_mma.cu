@@ -5,7 +5,7 @@ namespace t2n {
 int launch_app_forward_mma(const AppMmaArgs& a, int smem_bytes, int grid, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(app_forward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return (int)e;
-    app_forward_mma_kernel<<<grid, 256, smem_bytes, st>>>(a);
+    app_forward_mma_kernel<<<grid, kMmaThreads, smem_bytes, st>>>(a);
     return (int)cudaGetLastError();
 }
 int launch_pack_mma(const AppArgs& a, const float* w1, const int32_t* perm, int K, float* out, cudaStream_t st) {
