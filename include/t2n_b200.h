@@ -32,7 +32,7 @@ extern "C" {
 
 typedef struct CUstream_st* t2n_stream_t;   /* == cudaStream_t */
 
-#define T2N_ABI_VERSION 4
+#define T2N_ABI_VERSION 5
 
 enum {
     T2N_E_BADARG   = -1,   /* null pointer / non-positive size */
@@ -73,6 +73,7 @@ typedef struct T2NField {
     int   n_app[3];             /* appearance_n_comp                   tensoRF.py:146 */
     int   mlp_in;               /* decoder input width (351 for MLP_Fea_noview fea_pe=6) */
     int   mlp_in_pad;           /* mlp_in rounded up to a multiple of 32 */
+    int   fea_pe, view_pe;      /* frequency counts of the feature / view-direction encodings (tensorBase.py:66,92) */
 } T2NField;
 
 /* Parameters (read-only in forward).  State-dict names in comments. */
@@ -220,6 +221,9 @@ int t2n_compute_alpha(const T2NField* field, const T2NParams* params, const T2NA
  * pairs of the most recent call: ids 0=march 1=pack_w1 2=appearance 3=finalize 4=app_backward
  * 5=unpack_w1_grad 6=ray_backward.  Returns the number of pairs written. */
 int t2n_profile_enable(int on);
+/* Debug aid: with T2N_MMA_TRACE set in the environment the tensor-core appearance kernel's CTA 0 writes
+ * 32 cycle counters (stage times, barrier waits); this copies them to the host.  Returns 32 or 0. */
+int t2n_debug_trace_read(long long* out32);
 int t2n_profile_read(int* ids, float* ms, int n);
 
 #ifdef __cplusplus

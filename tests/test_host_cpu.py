@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     # natural alignment, no packing surprises: sizes are what the C compiler produces for the header
-    assert C.sizeof(nat.T2NField) == 4 * (9 + 3 + 1 + 2 + 4 + 4 + 6 + 2)
+    assert C.sizeof(nat.T2NField) == 4 * (9 + 3 + 1 + 2 + 4 + 4 + 6 + 2 + 2)
     assert C.sizeof(nat.T2NParams) == 8 * (12 + 1 + 6 + 2)
     assert C.sizeof(nat.T2NGrads) == 8 * (12 + 1 + 6)
     assert C.sizeof(nat.T2NBatch) == 8 * 2 + 4 * 4

@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libt2n_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class NativeLibraryError(RuntimeError):
@@ -35,6 +35,7 @@ class T2NField(C.Structure):
         ("act", C.c_int), ("shading", C.c_int), ("app_dim", C.c_int), ("feature_c", C.c_int),
         ("n_sigma", I3), ("n_app", I3),
         ("mlp_in", C.c_int), ("mlp_in_pad", C.c_int),
+        ("fea_pe", C.c_int), ("view_pe", C.c_int),
     ]
 
 
@@ -95,6 +96,7 @@ SYMBOLS = {
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "t2n_rotate_rays": (C.c_int, [C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "t2n_profile_enable": (C.c_int, [C.c_int]),
+    "t2n_debug_trace_read": (C.c_int, [C.POINTER(C.c_longlong)]),
     "t2n_profile_read": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
     "t2n_compute_alpha": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
                                     C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),

@@ -80,11 +80,12 @@ FieldDev make_field_dev(const T2NField* f, const T2NAlphaMask* mask) {
     return d;
 }
 
-bool mma_eligible(const T2NField* f) {
-    if (f->shading > T2N_SHADE_MLP || f->feature_c != 128 || f->app_dim > 32) return false;
+bool mma_recipe(const T2NField* f, MmaRecipe& R) {
+    if (f->shading > T2N_SHADE_MLP || f->feature_c != 128) return false;
     int tot = 0;
     for (int i = 0; i < 3; ++i) { if (f->n_app[i] % 16) return false; tot += f->n_app[i]; }
-    return tot <= 160 && f->mlp_in_pad % 32 == 0;
+    if (tot > 160) return false;
+    return build_mma_recipe(f->shading, f->app_dim, f->fea_pe, f->view_pe, R);
 }
 
 int max_quads(const int n[3]) {
@@ -117,6 +118,7 @@ struct Profiler {
     }
 };
 Profiler g_prof;
+long long* g_trace = nullptr;
 
 AppArgs make_app_args(const T2NField* f, const T2NParams* p, const FieldDev& fd, const T2NBatch* b,
                       const T2NOutputs* out, const T2NScratch* s) {
@@ -160,14 +162,20 @@ const char* t2n_error_string(int code) {
 }
 
 size_t t2n_mma_pack_floats(const T2NField* field) {
-    if (!field || !mma_eligible(field)) return 0;
-    return mma_pack_layout(field->n_app[0] + field->n_app[1] + field->n_app[2], field->mlp_in_pad).total;
+    MmaRecipe R;
+    if (!field || !mma_recipe(field, R)) return 0;
+    return mma_pack_layout(field->n_app[0] + field->n_app[1] + field->n_app[2], R.Kp).total;
 }
 
 int t2n_profile_enable(int on) {
     g_prof.on = on != 0;
     g_prof.n = 0;
     return 0;
+}
+
+int t2n_debug_trace_read(long long* out32) {
+    if (!g_trace || !out32) return 0;
+    return cudaMemcpy(out32, g_trace, 32 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 32 : 0;
 }
 
 int t2n_profile_read(int* ids, float* ms, int n) {
@@ -241,18 +249,27 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
     // ---- K2
     {
         AppArgs aa = make_app_args(field, params, fd, batch, out, scratch);
-        const bool use_mma = scratch->mma_pack != nullptr && mma_eligible(field);
+        MmaRecipe R;
+        const bool use_mma = scratch->mma_pack != nullptr && mma_recipe(field, R);
         if (use_mma) {
             g_prof.start(1, st);
-            rc = launch_pack_mma(aa, params->w1, params->col_perm, field->mlp_in, scratch->mma_pack, st);
+            rc = launch_pack_mma(aa, R, params->w1, field->mlp_in, scratch->mma_pack, st);
             g_prof.stop(st);
             if (rc) return rc;
             AppMmaArgs ma2;
+            memset(&ma2, 0, sizeof(ma2));
             ma2.fw = aa;
             ma2.pack = scratch->mma_pack;
+            ma2.n_freq = R.n_freq; ma2.pe_chunks = R.pe_chunks; ma2.Kp = R.Kp;
+            memcpy(ma2.ident_src, R.ident_src, 32); memcpy(ma2.pe_src, R.pe_src, 32); memcpy(ma2.pe_nf, R.pe_nf, 32);
             const char* tenv = getenv("T2N_MMA_TERMS");          // accuracy study hook; default 3xTF32
             ma2.terms = tenv ? atoi(tenv) : 7;
-            const int smem_bytes = mma_smem_layout(aa.Kp).total;
+            if (getenv("T2N_MMA_TRACE")) {                       // debug cycle counters of CTA 0
+                if (!g_trace) cudaMalloc(&g_trace, 32 * sizeof(long long));
+                cudaMemsetAsync(g_trace, 0, 32 * sizeof(long long), st);
+                ma2.trace = g_trace;
+            }
+            const int smem_bytes = mma_smem_layout().total;
             if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
             g_prof.start(2, st);
             rc = launch_app_forward_mma(ma2, smem_bytes, dev.sm_count, st);

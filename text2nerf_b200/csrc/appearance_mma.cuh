@@ -12,14 +12,17 @@
 //      B chunk  [N rows   ][32 k]  hi + lo, pre-swizzled images in global memory written by
 //               pack_mma_weights_kernel, fetched by ONE TMA bulk copy per chunk (2-stage ring)
 // and four "groups" of chunks run back to back per tile:
-//      G0  basis   : A = plane*line products (gather), 5 chunks, N = 32   -> D0  (TMEM cols 128..159)
-//      G1  layer 1 : A = decoder input columns (recipe: identity | sin,cos pairs), Kp/32 chunks,
-//                    N = 128                                                -> D1  (cols 0..127)
-//      G2  layer 2 : A = relu(D1 + b1) read back from TMEM chunk by chunk, 4 chunks, N = 128
+//      S0  basis   : A = plane*line products (gather), 5 chunks, N = 32   -> D0  (TMEM cols 256..287)
+//      S1  layer 1 : A = decoder input columns, frequency-major (MmaRecipe), 13 chunks for the
+//                    configured head, N = 128                               -> D1  (cols 0..127)
+//      S2  layer 2 : A = relu(D1 + b1) read back from TMEM chunk by chunk, 4 chunks, N = 128
 //                                                                           -> D2  (cols 128..255)
-//      E2  layer 3 + sigmoid on the CUDA cores straight out of TMEM.
-// The producer of chunk c+1 overlaps the asynchronous MMAs of chunk c; mbarriers track
-// "B landed" (TMA complete_tx), "stage free" and "accumulator complete" (tcgen05.commit).
+//      S3  layer 3 + sigmoid on the CUDA cores straight out of TMEM.
+// The stages of THREE consecutive tiles are software-pipelined -- iteration j runs S2(j-2), S1(j-1),
+// S0(j), S3(j-2) -- so no stage ever waits for the accumulator it has just fed: by the time a tile's
+// next stage starts, a whole other stage of another tile has been produced in between.  The producer
+// of chunk c+1 also overlaps the asynchronous MMAs of chunk c; mbarriers track "B landed" (TMA
+// complete_tx), "A written", "stage free" and "accumulator complete" (tcgen05.commit).
 #pragma once
 #include "appearance_mma_defs.cuh"
 
@@ -66,9 +69,74 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
+// A operand from tensor memory (lane = row, column = k), B from shared memory: halves the shared-memory
+// operand traffic of the 3xTF32 decoder GEMMs, which otherwise bounds the kernel (12 MMAs x 8 KB per chunk)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// split 8 fp32 values into TF32 hi / lo and store them as columns [col, col+8) of a TMEM A stage (hi | lo)
+__device__ __forceinline__ void st_split8_tmem(uint32_t a_stage_lane, int col, const float (&v)[8]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        h[q] = tf32_hi(v[q]);
+        l[q] = __float_as_uint(v[q] - __uint_as_float(h[q]));
+    }
+    tmem_st8(a_stage_lane + col, h);
+    tmem_st8(a_stage_lane + 32 + col, l);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// ---- warp-uniform issue path -----------------------------------------------------------------------
+// The issuer warp stays converged and every lane executes these; `elect.sync` picks the one lane that
+// actually issues.  With uniform control flow ptxas keeps descriptors in uniform registers and the
+// tensor pipe runs at its nominal 64 cycles per 128x128x8 TF32 MMA; issuing from a divergent
+// `if (lane == 0)` branch costs ~170 cycles per MMA (tools/mma_rate.cu, measured on B200).
+__device__ __forceinline__ void umma_ss_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        :: "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+        :: "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_elect(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+        :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar_addr) : "memory");
+}
+// low 32 bits of a SWIZZLE_128B K-major descriptor (start address | LBO); the high word is constant
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3fffu) | (1u << 16); }
+constexpr uint32_t kDescHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));   // SBO | version | SWIZZLE_128B
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -88,8 +156,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 
 // One thread per (matrix, chunk, row, 16-byte column group): writes hi and lo swizzled images.
+struct PackPerm { short perm[32 * (1 + 2 * kMaxFreq)]; };
 static __global__ void pack_mma_weights_kernel(const float* __restrict__ basis, int app_dim, int n_app_total,
-                                               const float* __restrict__ w1, const int32_t* __restrict__ perm, int K,
+                                               const float* __restrict__ w1, const __grid_constant__ PackPerm perm, int K,
                                                int Kp, const float* __restrict__ w2, float* __restrict__ out) {
     const MmaPack P = mma_pack_layout(n_app_total, Kp);
     const int total_groups = (P.basis_chunks * 32 + P.w1_chunks * 128 + P.w2_chunks * 128) * 8;
@@ -112,7 +181,7 @@ static __global__ void pack_mma_weights_kernel(const float* __restrict__ basis, 
         const int c = rowid / 128; r = rowid % 128; rows = 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int src = perm[c * 32 + j * 4 + q];
+            const int src = perm.perm[c * 32 + j * 4 + q];
             v[q] = src >= 0 ? w1[(size_t)r * K + src] : 0.f;
         }
         dst_hi = out + P.w1_off + (size_t)c * 2 * 128 * 32;
@@ -151,16 +220,28 @@ __device__ __forceinline__ void issue_chunk(uint32_t a_stage, uint32_t b_stage, 
         if (terms & 4) umma_tf32(tmem_d, dah, dbl, idesc, true);
     }
 }
+// same with the A chunk in tensor memory (stage = 64 columns: hi | lo)
+__device__ __forceinline__ void issue_chunk_ts(uint32_t a_tmem, uint32_t b_stage, uint32_t tmem_d, uint32_t idesc,
+                                               bool first_chunk, int terms) {
+    const uint32_t b_hi = b_stage, b_lo = b_stage + 128u * 128u;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t dbh = umma_desc_sw128(b_hi + kk * 32), dbl = umma_desc_sw128(b_lo + kk * 32);
+        umma_tf32_ts(tmem_d, a_tmem + kk * 8, dbh, idesc, !(first_chunk && kk == 0));
+        if (terms & 2) umma_tf32_ts(tmem_d, a_tmem + 32 + kk * 8, dbh, idesc, true);
+        if (terms & 4) umma_tf32_ts(tmem_d, a_tmem + kk * 8, dbl, idesc, true);
+    }
+}
 
-// Requirements (checked by the host): MLP shading, feature_c == 128, app_dim <= 32, every n_app[i] a
+// Requirements (checked by the host): MLP shading, feature_c == 128, app_dim <= 29, every n_app[i] a
 // multiple of 16, sum(n_app) <= 160.
 //
 // Warp roles: warps 0..15 (512 threads) are PRODUCERS/EPILOGUES -- they build the A chunks (gather,
 // decoder columns, relu(D1+b1)) and read the accumulators; warp 16 lane 0 is the ISSUER -- it streams
 // the B chunks with TMA bulk copies and issues every tcgen05.mma.  The two sides only meet on
-// mbarriers (a_full: 16 warp arrivals, b_full: TMA bytes, free/acc: tcgen05.commit), so producing chunk
-// c+1 overlaps the MMAs of chunk c with no CTA-wide barrier in the chunk loops.  The producer work is
-// dependent-latency bound (ncu: 25 % issue utilisation with 8 warps), hence 16 warps per CTA.
+// mbarriers (a_full: 16 warp arrivals, b_full: TMA bytes, free/acc: tcgen05.commit) and both walk the
+// same chunk sequence, so there is no CTA-wide barrier in the chunk loops.
+static_assert(kNB == 4, "bar_done ring assumes a 4-deep B ring");
 constexpr int kProdWarps = 16;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kMmaThreads = kProdThreads + 32;
@@ -172,35 +253,35 @@ __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;
 __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const __grid_constant__ AppMmaArgs args) {
     extern __shared__ uint8_t smem_raw[];
     const AppArgs& a = args.fw;
-    const MmaSmem L = mma_smem_layout(a.Kp);
+    const MmaSmem L = mma_smem_layout();
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_addr = smem_u32(sm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = a.counters[0];
-    const MmaPack P = mma_pack_layout(a.n_app_total, a.Kp);
+    const MmaPack P = mma_pack_layout(a.n_app_total, args.Kp);
 
     float* base = reinterpret_cast<float*>(sm + L.base);
     float* b1s = reinterpret_cast<float*>(sm + L.b1);
     float* b2s = reinterpret_cast<float*>(sm + L.b2);
     float* w3s = reinterpret_cast<float*>(sm + L.w3);
     float* b3s = reinterpret_cast<float*>(sm + L.b3);
-    int* pairs = reinterpret_cast<int*>(sm + L.pairs);
     float* part = reinterpret_cast<float*>(sm + L.part);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
-    uint64_t* bar_bfull = bars;         // [2] B chunk landed (TMA complete_tx)
-    uint64_t* bar_free = bars + 2;      // [2] MMAs reading stage s have completed (tcgen05.commit)
-    uint64_t* bar_acc = bars + 4;       // accumulator of the current group complete (tcgen05.commit)
-    uint64_t* bar_afull = bars + 5;     // [2] A chunk written by all 8 producer warps
+    uint64_t* bar_bfull = bars;         // [kNB] B chunk landed (TMA complete_tx)
+    uint64_t* bar_done = bars + 4;      // [4] MMAs of chunk it (slot it % 4) have completed (tcgen05.commit): frees A stage
+                                        //     it & 1 for the producers and B stage it % kNB for the weight prefetcher
+    uint64_t* bar_afull = bars + 10;    // [2] A chunk written by all 16 producer warps
+    uint64_t* bar_acc = bars + 12;      // [3] accumulator D0 / D1 / D2 of a tile complete (tcgen05.commit)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
 
-    for (int i = tid; i < a.Kp / 2; i += kMmaThreads) pairs[i] = __ldg(a.pair_desc + i);
     for (int i = tid; i < 128; i += kMmaThreads) { b1s[i] = __ldg(a.b1 + i); b2s[i] = __ldg(a.b2 + i); }
     for (int i = tid; i < 3 * 128; i += kMmaThreads) w3s[i] = __ldg(a.w3 + i);
     if (tid < 3) b3s[tid] = __ldg(a.b3 + tid);
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 10; ++i) mbar_init(bars + i, 1);
         mbar_init(bar_afull + 0, kProdWarps);
         mbar_init(bar_afull + 1, kProdWarps);
+        for (int i = 0; i < 3; ++i) mbar_init(bar_acc + i, 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -213,54 +294,104 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
     const uint32_t tmem = *tmem_slot;
 
     const int nk0 = P.basis_chunks, nk1 = P.w1_chunks, nk2 = P.w2_chunks;
-    const int per_tile = nk0 + nk1 + nk2;
+    int n_tiles = 0;
+    for (int tile = blockIdx.x; tile * kMmaM < total; tile += gridDim.x) ++n_tiles;
 
     if (warp == kProdWarps) {
         // =========================== ISSUER ===========================
-        if (lane == 0) {
+        if (n_tiles > 0) {
             const uint32_t idesc128 = umma_idesc_tf32(128), idesc32 = umma_idesc_tf32(32);
+            const uint32_t tm = __shfl_sync(T2N_FULL, tmem, 0);
+            const uint32_t smb = __shfl_sync(T2N_FULL, sm_addr, 0);
+            const uint32_t bars_addr = smb + L.bars;
+            const int terms = args.terms;
+            // the chunk sequence both sides walk: iteration j = [S2 of tile j-2][S1 of tile j-1][S0 of tile j]
             uint32_t it = 0, loaded = 0;
-            int n_tiles = 0;
-            for (int tile = blockIdx.x; tile * kMmaM < total; tile += gridDim.x) ++n_tiles;
-            const uint32_t n_chunks = (uint32_t)n_tiles * per_tile;
-            auto chunk_src = [&](uint32_t i, const float*& src, uint32_t& bytes) {
-                const int c = (int)(i % per_tile);
-                if (c < nk0) { src = args.pack + P.basis_off + (size_t)c * 2 * 32 * 32; bytes = 2 * 32 * 128; }
-                else if (c < nk0 + nk1) { src = args.pack + P.w1_off + (size_t)(c - nk0) * 2 * 128 * 32; bytes = 2 * kTileBytes; }
-                else { src = args.pack + P.w2_off + (size_t)(c - nk0 - nk1) * 2 * 128 * 32; bytes = 2 * kTileBytes; }
+            int lj = 0, lg = 0, lc = 0;         // cursor of the B prefetcher: iteration, group (0=S2,1=S1,2=S0), chunk
+            auto group_valid = [&](int j, int g) {
+                const int t = j - (2 - g);      // g=0 -> tile j-2, g=1 -> tile j-1, g=2 -> tile j
+                return t >= 0 && t < n_tiles;
             };
-            auto prefetch = [&](uint32_t upto) {        // issue B loads for chunks < upto whose stage is free
-                while (loaded < upto && loaded < n_chunks) {
-                    if (loaded >= 2) mbar_wait(bar_free + (loaded & 1), ((loaded >> 1) - 1) & 1);
-                    const float* src; uint32_t bytes;
-                    chunk_src(loaded, src, bytes);
-                    mbar_expect_tx(bar_bfull + (loaded & 1), bytes);
-                    tma_bulk_g2s(sm + L.b[loaded & 1], src, bytes, bar_bfull + (loaded & 1));
-                    ++loaded;
+            auto group_len = [&](int g) { return g == 0 ? nk2 : (g == 1 ? nk1 : nk0); };
+            auto advance = [&](int& j, int& g, int& c) {      // move the cursor to the next existing chunk
+                ++c;
+                while (j < n_tiles + 2 && (!group_valid(j, g) || c >= group_len(g))) {
+                    c = 0;
+                    if (++g == 3) { g = 0; ++j; }
                 }
             };
-            prefetch(1);
-            for (; it < n_chunks; ++it) {
-                const int c = (int)(it % per_tile);
-                mbar_wait(bar_afull + (it & 1), (it >> 1) & 1);
-                mbar_wait(bar_bfull + (it & 1), (it >> 1) & 1);
-                tc_fence_after();
-                uint32_t d, idesc; int rows; bool first, last;
-                if (c < nk0) { d = tmem + kColD0; idesc = idesc32; rows = 32; first = c == 0; last = c == nk0 - 1; }
-                else if (c < nk0 + nk1) { d = tmem + kColD1; idesc = idesc128; rows = 128; first = c == nk0; last = c == nk0 + nk1 - 1; }
-                else { d = tmem + kColD2; idesc = idesc128; rows = 128; first = c == nk0 + nk1; last = c == per_tile - 1; }
-                issue_chunk(sm_addr + L.a[it & 1], sm_addr + L.b[it & 1], rows, d, idesc, first, args.terms);
-                umma_commit(bar_free + (it & 1));
-                if (last) umma_commit(bar_acc);
-                prefetch(it + 2);                       // B of the next chunk lands while this one computes
+            while (lj < n_tiles + 2 && !group_valid(lj, lg)) { if (++lg == 3) { lg = 0; ++lj; } }
+            auto prefetch = [&](uint32_t upto) {        // issue B loads for chunks < upto whose stage is free
+                while (loaded < upto && lj < n_tiles + 2) {
+                    const uint32_t bs = loaded % kNB;
+                    if (loaded >= kNB) mbar_wait(bar_done + bs, ((loaded / kNB) - 1) & 1);
+                    const float* src; uint32_t bytes;
+                    if (lg == 2) { src = args.pack + P.basis_off + (size_t)lc * 2 * 32 * 32; bytes = 2 * 32 * 128; }
+                    else if (lg == 1) { src = args.pack + P.w1_off + (size_t)lc * 2 * 128 * 32; bytes = 2 * kTileBytes; }
+                    else { src = args.pack + P.w2_off + (size_t)lc * 2 * 128 * 32; bytes = 2 * kTileBytes; }
+                    tma_load_elect(smb + L.b[bs], src, bytes, bars_addr + 8 * bs);
+                    ++loaded;
+                    advance(lj, lg, lc);
+                }
+            };
+            const bool tr = args.trace != nullptr && blockIdx.x == 0 && lane == 0;
+            long long w_af = 0, w_bf = 0, t_is = 0, t_pf = 0, t0i = clock64();
+            prefetch(kNB - 1);
+            for (int j = 0; j < n_tiles + 2; ++j)
+                for (int g = 0; g < 3; ++g) {
+                    if (!group_valid(j, g)) continue;
+                    const int len = group_len(g);
+                    const uint32_t d = tm + (g == 0 ? kColD2 : (g == 1 ? kColD1 : kColD0));
+                    const uint32_t idesc = g == 2 ? idesc32 : idesc128;
+                    for (int c = 0; c < len; ++c, ++it) {
+                        const uint32_t bs = it % kNB;
+                        long long c0 = clock64();
+                        mbar_wait(bar_bfull + bs, (it / kNB) & 1);
+                        long long c1 = clock64();
+                        mbar_wait(bar_afull + (it & 1), (it >> 1) & 1);
+                        long long c2 = clock64();
+                        tc_fence_after();
+                        const uint32_t bh = desc_lo(smb + L.b[bs]);
+                        if (g == 2) {                       // basis: A from shared memory, N = 32 (B tile 32 rows)
+                            const uint32_t ah = desc_lo(smb + L.a[it & 1]), al = ah + (kTileBytes >> 4), bl = bh + ((32 * 128) >> 4);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                umma_ss_elect(d, ah + 2 * kk, bh + 2 * kk, kDescHi, idesc, (c | kk) != 0);
+                                if (terms & 2) umma_ss_elect(d, al + 2 * kk, bh + 2 * kk, kDescHi, idesc, 1);
+                                if (terms & 4) umma_ss_elect(d, ah + 2 * kk, bl + 2 * kk, kDescHi, idesc, 1);
+                            }
+                        } else {                            // decoder layers: A from tensor memory (hi | lo), N = 128
+                            const uint32_t ta = tm + kColA + 64 * (it & 1), bl = bh + (kTileBytes >> 4);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc, (c | kk) != 0);
+                                if (terms & 2) umma_ts_elect(d, ta + 32 + 8 * kk, bh + 2 * kk, kDescHi, idesc, 1);
+                                if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc, 1);
+                            }
+                        }
+                        umma_commit_elect(bars_addr + 8 * (4 + bs));               // bar_done[it % 4]
+                        if (c == len - 1) umma_commit_elect(bars_addr + 8 * (12 + (2 - g)));   // bar_acc: g=0 -> D2, 1 -> D1, 2 -> D0
+                        long long c3 = clock64();
+                        prefetch(it + kNB - 1);         // chunk it+2 reuses the B stage of chunk it-2 (long done): no stall
+                        long long c4 = clock64();
+                        w_bf += c1 - c0; w_af += c2 - c1; t_is += c3 - c2; t_pf += c4 - c3;
+                    }
+                }
+            if (tr) {
+                args.trace[16] = clock64() - t0i; args.trace[17] = w_bf; args.trace[18] = w_af; args.trace[19] = t_is;
+                args.trace[20] = t_pf; args.trace[21] = it; args.trace[22] = n_tiles;
             }
         }
     } else {
         // =========================== PRODUCERS ===========================
+        const bool tr = args.trace != nullptr && blockIdx.x == 0 && tid == 0;
+        long long tS[4] = {0, 0, 0, 0}, wAcc[3] = {0, 0, 0}, wSt[3] = {0, 0, 0}, t0p = clock64();
+        int cur_stage = 0;
         uint32_t it = 0;        // chunks produced so far by this CTA (ring position)
-        uint32_t acc_n = 0;     // accumulator-complete events consumed so far
         auto stage_acquire = [&](uint32_t i) {
-            if (i >= 2) mbar_wait(bar_free + (i & 1), ((i >> 1) - 1) & 1);
+            const long long c0 = clock64();
+            if (i >= 2) mbar_wait(bar_done + ((i - 2) & 3), ((i - 2) >> 2) & 1);    // chunk i-2 used this A stage
+            wSt[cur_stage] += clock64() - c0;
         };
         auto stage_publish = [&](uint32_t i) {          // generic-proxy writes -> async proxy, then one arrival per warp
             fence_async_smem();
@@ -268,20 +399,119 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_afull + (i & 1));
         };
-        auto acc_wait = [&]() {
-            mbar_wait(bar_acc, acc_n & 1);
-            ++acc_n;
+        auto stage_publish_tmem = [&](uint32_t i) {     // tcgen05.st writes complete, then one arrival per warp
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afull + (i & 1));
+        };
+        auto acc_wait = [&](int which, int local_tile) {     // accumulator `which` (0=D0,1=D1,2=D2) of the CTA's n-th tile
+            const long long c0 = clock64();
+            mbar_wait(bar_acc + which, local_tile & 1);
+            wAcc[which] += clock64() - c0;
             tc_fence_after();
         };
-        const int row = tid >> 2, sub = tid & 3;            // G0 mapping: 4 threads per point, 8 channels each
+        const int row = tid >> 2, sub = tid & 3;            // S0 mapping: 4 threads per point, 8 channels each
         const int erow = 32 * (warp & 3) + lane;            // epilogue mapping: TMEM lane = row
         const int eq = warp >> 2;                           // column quarter handled by this warp
         const uint32_t tmem_lane = (uint32_t)(32 * (warp & 3)) << 16;
+        const int m1 = tid & 127, ph = tid >> 7;            // S1 mapping: row, entry group
+        // S1: the 8 decoder entries this thread owns: 4ph..4ph+3 (first half chunk) and 16+4ph.. (second)
+        int ent_src[8], ent_nf[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = (q < 4) ? (4 * ph + q) : (16 + 4 * ph + (q - 4));
+            ent_src[q] = args.pe_src[e];
+            ent_nf[q] = args.pe_nf[e];
+        }
+        int id_src[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) id_src[q] = args.ident_src[8 * ph + q];
 
-        for (int tile = blockIdx.x; tile * kMmaM < total; tile += gridDim.x) {
-            const int e0 = tile * kMmaM;
-            // ================= G0: gather -> products -> basis MMA =================
-            {
+        for (int j = 0; j < n_tiles + 2; ++j) {
+            // ================= S2(j-2): relu(D1 + b1) -> layer 2 =================
+            long long ts0 = clock64();
+            if (j - 2 >= 0 && j - 2 < n_tiles) {
+                cur_stage = 0;
+                acc_wait(1, j - 2);
+                for (int c = 0; c < nk2; ++c, ++it) {
+                    uint32_t v[8];
+                    const int col0 = c * 32 + eq * 8;
+                    tmem_ld8(tmem + tmem_lane + kColD1 + col0, v);
+                    float h[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) h[q] = fmaxf(__uint_as_float(v[q]) + b1s[col0 + q], 0.f);
+                    stage_acquire(it);
+                    st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it & 1), eq * 8, h);
+                    stage_publish_tmem(it);
+                }
+            }
+            // ================= S1(j-1): feature from D0, decoder input columns -> layer 1 =================
+            long long ts1 = clock64(); tS[2] += ts1 - ts0;
+            if (j - 1 >= 0 && j - 1 < n_tiles) {
+                cur_stage = 1;
+                acc_wait(0, j - 1);
+                if (warp < 4) {
+                    uint32_t v[16];
+                    float* brow = base + erow * kBaseStride;
+                    tmem_ld16(tmem + tmem_lane + kColD0, v);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) if (q < a.app_dim) brow[q] = __uint_as_float(v[q]);
+                    tmem_ld16(tmem + tmem_lane + kColD0 + 16, v);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) if (16 + q < a.app_dim) brow[16 + q] = __uint_as_float(v[q]);
+                }
+                tc_fence_before();
+                producers_sync();
+                const float* brow = base + m1 * kBaseStride;
+                // chunk 0: identity columns 8ph .. 8ph+7
+                {
+                    float c0[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) c0[q] = brow[id_src[q]];
+                    stage_acquire(it);
+                    st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it & 1), 8 * ph, c0);
+                    stage_publish_tmem(it);
+                    ++it;
+                }
+                // frequency blocks: one precise sincosf per owned entry, then angle doubling
+                float sn[8], cs[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    sn[q] = 0.f; cs[q] = 1.f;
+                    if (ent_nf[q] > 0) sincosf(brow[ent_src[q]], &sn[q], &cs[q]);
+                }
+                for (int f = 0; f < args.n_freq; ++f) {
+                    if (f > 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float s2 = 2.f * sn[q];
+                            const float ns = s2 * cs[q];
+                            cs[q] = fmaf(-s2, sn[q], 1.f);
+                            sn[q] = ns;
+                        }
+                    }
+                    for (int h = 0; h < args.pe_chunks; ++h, ++it) {
+                        float cols[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            cols[2 * q] = h ? sn[4 + q] : sn[q];
+                            cols[2 * q + 1] = h ? cs[4 + q] : cs[q];
+                        }
+                        stage_acquire(it);
+                        st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it & 1), 8 * ph, cols);
+                        stage_publish_tmem(it);
+                    }
+                }
+            }
+            // ================= S0(j): gather -> products -> basis MMA =================
+            long long ts2 = clock64(); tS[1] += ts2 - ts1;
+            if (j < n_tiles) {
+                cur_stage = 2;
+                // heads with view-direction columns read base[viewdir] in S1; do not let fast warps
+                // overwrite it with the next tile's directions before everybody is through S1
+                if (a.shading != T2N_SHADE_MLP_FEA_NOVIEW) producers_sync();
+                const int e0 = (blockIdx.x + j * gridDim.x) * kMmaM;
                 const int e = e0 + row;
                 const bool live = e < total;
                 Axis ax[3];
@@ -349,100 +579,55 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                     for (int q = 0; q < 2; ++q) st_split4(A_hi, A_lo, sw128_off(row, sub * 2 + q), prod[q]);
                     stage_publish(it);
                 }
-                // epilogue 0: feature = D0[:, 0:app_dim] -> base vector (fp32)
-                acc_wait();
-                if (warp < 4) {
-                    uint32_t v[16];
-                    float* brow = base + erow * kBaseStride;
-                    tmem_ld16(tmem + tmem_lane + kColD0, v);
+            }
+            // ================= S3(j-2): relu(D2 + b2) . W3 + b3 -> sigmoid =================
+            long long ts3 = clock64(); tS[0] += ts3 - ts2;
+            if (j - 2 >= 0 && j - 2 < n_tiles) {
+                const int e0 = (blockIdx.x + (j - 2) * gridDim.x) * kMmaM;
+                acc_wait(2, j - 2);
+                {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) if (q < a.app_dim) brow[q] = __uint_as_float(v[q]);
-                    tmem_ld16(tmem + tmem_lane + kColD0 + 16, v);
+                    for (int blk = 0; blk < 2; ++blk) {
+                        uint32_t v[16];
+                        const int col0 = eq * 32 + blk * 16;
+                        tmem_ld16(tmem + tmem_lane + kColD2 + col0, v);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) if (16 + q < a.app_dim) brow[16 + q] = __uint_as_float(v[q]);
+                        for (int q = 0; q < 16; ++q) {
+                            const float h = fmaxf(__uint_as_float(v[q]) + b2s[col0 + q], 0.f);
+                            s0 = fmaf(h, w3s[col0 + q], s0);
+                            s1 = fmaf(h, w3s[128 + col0 + q], s1);
+                            s2 = fmaf(h, w3s[256 + col0 + q], s2);
+                        }
+                    }
+                    float* pp = part + (erow * 4 + eq) * 4;
+                    pp[0] = s0; pp[1] = s1; pp[2] = s2;
                 }
                 tc_fence_before();
                 producers_sync();
-            }
-            // ================= G1: decoder input columns -> layer 1 =================
-            {
-                const int m = tid & 127, ph = tid >> 7;         // 4 pairs (8 columns) per thread per chunk
-                const float* brow = base + m * kBaseStride;
-                for (int c = 0; c < nk1; ++c, ++it) {
-                    float4 cols[2];
-                    TrigChain tc;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int pj = c * 16 + ph * 4 + q * 2;
-                        const float2 u = decoder_pair(pairs[pj], brow, tc);
-                        const float2 w = decoder_pair(pairs[pj + 1], brow, tc);
-                        cols[q] = make_float4(u.x, u.y, w.x, w.y);
-                    }
-                    stage_acquire(it);
-                    uint8_t* A_hi = sm + L.a[it & 1];
-                    uint8_t* A_lo = A_hi + kTileBytes;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) st_split4(A_hi, A_lo, sw128_off(m, ph * 2 + q), cols[q]);
-                    stage_publish(it);
-                }
-            }
-            // ================= G2: relu(D1 + b1) -> layer 2 =================
-            acc_wait();
-            for (int c = 0; c < nk2; ++c, ++it) {
-                uint32_t v[8];
-                const int col0 = c * 32 + eq * 8;
-                tmem_ld8(tmem + tmem_lane + kColD1 + col0, v);
-                float4 h[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    h[q].x = fmaxf(__uint_as_float(v[4 * q + 0]) + b1s[col0 + 4 * q + 0], 0.f);
-                    h[q].y = fmaxf(__uint_as_float(v[4 * q + 1]) + b1s[col0 + 4 * q + 1], 0.f);
-                    h[q].z = fmaxf(__uint_as_float(v[4 * q + 2]) + b1s[col0 + 4 * q + 2], 0.f);
-                    h[q].w = fmaxf(__uint_as_float(v[4 * q + 3]) + b1s[col0 + 4 * q + 3], 0.f);
-                }
-                stage_acquire(it);
-                uint8_t* A_hi = sm + L.a[it & 1];
-                uint8_t* A_lo = A_hi + kTileBytes;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) st_split4(A_hi, A_lo, sw128_off(erow, eq * 2 + q), h[q]);
-                stage_publish(it);
-            }
-            // ================= E2: relu(D2 + b2) . W3 + b3 -> sigmoid =================
-            acc_wait();
-            {
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {
-                    uint32_t v[16];
-                    const int col0 = eq * 32 + blk * 16;
-                    tmem_ld16(tmem + tmem_lane + kColD2 + col0, v);
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const float h = fmaxf(__uint_as_float(v[q]) + b2s[col0 + q], 0.f);
-                        s0 = fmaf(h, w3s[col0 + q], s0);
-                        s1 = fmaf(h, w3s[128 + col0 + q], s1);
-                        s2 = fmaf(h, w3s[256 + col0 + q], s2);
+                if (tid < kMmaM * 3) {
+                    const int m = tid / 3, c = tid - m * 3;
+                    const int e = e0 + m;
+                    if (e < total) {
+                        const float* pm = part + m * 16 + c;
+                        const float s = (pm[0] + pm[4]) + (pm[8] + pm[12]) + b3s[c];
+                        a.app_rgb[(size_t)e * 3 + c] = 1.f / (1.f + expf(-s));
                     }
                 }
-                float* pp = part + (erow * 4 + eq) * 4;
-                pp[0] = s0; pp[1] = s1; pp[2] = s2;
+                producers_sync();
             }
-            tc_fence_before();
-            producers_sync();
-            if (tid < kMmaM * 3) {
-                const int m = tid / 3, c = tid - m * 3;
-                const int e = e0 + m;
-                if (e < total) {
-                    const float* pm = part + m * 16 + c;
-                    const float s = (pm[0] + pm[4]) + (pm[8] + pm[12]) + b3s[c];
-                    a.app_rgb[(size_t)e * 3 + c] = 1.f / (1.f + expf(-s));
-                }
-            }
-            producers_sync();
+            tS[3] += clock64() - ts3;
+        }
+        if (tr) {
+            args.trace[0] = clock64() - t0p;
+            for (int q = 0; q < 4; ++q) args.trace[1 + q] = tS[q];      // S0, S1, S2, S3 (incl. their waits)
+            for (int q = 0; q < 3; ++q) args.trace[5 + q] = wAcc[q];    // waits for D0, D1, D2
+            for (int q = 0; q < 3; ++q) args.trace[8 + q] = wSt[q];     // A-stage waits inside S2, S1, S0
+            args.trace[11] = n_tiles;
         }
     }
 
-    // teardown: every group issued was waited on by the producers, so all MMAs have completed
+    // teardown: every accumulator that was committed has been waited on, so all MMAs have completed
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {

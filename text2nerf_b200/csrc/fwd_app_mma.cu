@@ -8,11 +8,12 @@ int launch_app_forward_mma(const AppMmaArgs& a, int smem_bytes, int grid, cudaSt
     app_forward_mma_kernel<<<grid, kMmaThreads, smem_bytes, st>>>(a);
     return (int)cudaGetLastError();
 }
-int launch_pack_mma(const AppArgs& a, const float* w1, const int32_t* perm, int K, float* out, cudaStream_t st) {
-    const MmaPack P = mma_pack_layout(a.n_app_total, a.Kp);
+int launch_pack_mma(const AppArgs& a, const MmaRecipe& R, const float* w1, int K, float* out, cudaStream_t st) {
+    const MmaPack P = mma_pack_layout(a.n_app_total, R.Kp);
     const int groups = (P.basis_chunks * 32 + P.w1_chunks * 128 + P.w2_chunks * 128) * 8;
-    pack_mma_weights_kernel<<<(groups + 255) / 256, 256, 0, st>>>(a.basis, a.app_dim, a.n_app_total, w1, perm, K, a.Kp,
-                                                               a.w2, out);
+    PackPerm pp;
+    for (int i = 0; i < (int)(sizeof(pp.perm) / sizeof(pp.perm[0])); ++i) pp.perm[i] = R.perm[i];
+    pack_mma_weights_kernel<<<(groups + 255) / 256, 256, 0, st>>>(a.basis, a.app_dim, a.n_app_total, w1, pp, K, R.Kp, a.w2, out);
     return (int)cudaGetLastError();
 }
 }  // namespace t2n

@@ -611,6 +611,7 @@ class TensorBase(torch.nn.Module):
             f.mlp_in, f.mlp_in_pad = mlp_in, len(perm)
         else:
             f.mlp_in, f.mlp_in_pad = 0, 32
+        f.fea_pe, f.view_pe = int(self.fea_pe), int(self.view_pe)
         self._field_cache = (self.shadingMode, f)
         return f
 
