@@ -32,7 +32,7 @@ extern "C" {
 
 typedef struct CUstream_st* t2n_stream_t;   /* == cudaStream_t */
 
-#define T2N_ABI_VERSION 5
+#define T2N_ABI_VERSION 7
 
 enum {
     T2N_E_BADARG   = -1,   /* null pointer / non-positive size */
@@ -154,6 +154,10 @@ typedef struct T2NOutputs {
  *   mma_pack   t2n_mma_pack_floats(field) float              pre-swizzled hi/lo TF32 operand images of
  *                                                            basis_mat, w1 and w2 for the tensor-core
  *                                                            decoder (NULL selects the FFMA decoder)
+ *   act_h1, act_h2  128*act_rows float each (optional, training) hidden activations relu(.) of the decoder per
+ *                                                            listed sample, written by the tensor-core forward so
+ *                                                            the backward does not recompute layers 1-2; when more
+ *                                                            than act_rows samples are listed the backward recomputes
  * A batch with R*S >= 2^31 is rejected with T2N_E_CAPACITY. */
 typedef struct T2NScratch {
     float*   sigma_feat;
@@ -169,6 +173,9 @@ typedef struct T2NScratch {
     int32_t* ray_flags;
     float*   w1_grad_packed;
     float*   mma_pack;
+    float*   act_h1;
+    float*   act_h2;
+    int64_t  act_rows;
 } T2NScratch;
 
 /* ---- entry points ------------------------------------------------------------------------ */

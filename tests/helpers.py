@@ -75,7 +75,7 @@ def render_with_jitter(model, rays, jitter, is_train, white_bg_effective, n_samp
     S = n_samples if n_samples > 0 else model.nSamples
     jit = None if jitter is None else jitter.reshape(-1).to(rays.device).contiguous()
     return _RenderFn.apply(model, rays.contiguous(), jit, S, bool(is_train), bool(white_bg_effective),
-                           *model._flat_params())
+                           torch.is_grad_enabled(), *model._flat_params())
 
 
 def rel_err(a, b, floor=0.0):

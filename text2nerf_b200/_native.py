@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libt2n_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 7
 
 
 class NativeLibraryError(RuntimeError):
@@ -77,7 +77,8 @@ class T2NScratch(C.Structure):
                 ("dsum", C.c_void_p), ("ray_start", C.c_void_p), ("ray_count", C.c_void_p),
                 ("slots", C.c_void_p), ("app_rgb", C.c_void_p), ("counters", C.c_void_p),
                 ("w1_packed", C.c_void_p), ("ray_flags", C.c_void_p), ("w1_grad_packed", C.c_void_p),
-                ("mma_pack", C.c_void_p)]
+                ("mma_pack", C.c_void_p), ("act_h1", C.c_void_p), ("act_h2", C.c_void_p),
+                ("act_rows", C.c_int64)]
 
 
 # every symbol include/t2n_b200.h declares, with its ctypes signature

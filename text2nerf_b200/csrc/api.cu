@@ -260,6 +260,7 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
             memset(&ma2, 0, sizeof(ma2));
             ma2.fw = aa;
             ma2.pack = scratch->mma_pack;
+            ma2.act_h1 = scratch->act_h1; ma2.act_h2 = scratch->act_h2; ma2.act_rows = scratch->act_rows;
             ma2.n_freq = R.n_freq; ma2.pe_chunks = R.pe_chunks; ma2.Kp = R.Kp;
             memcpy(ma2.ident_src, R.ident_src, 32); memcpy(ma2.pe_src, R.pe_src, 32); memcpy(ma2.pe_nf, R.pe_nf, 32);
             const char* tenv = getenv("T2N_MMA_TERMS");          // accuracy study hook; default 3xTF32
@@ -330,6 +331,7 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
             if (!b.gap[i] || !b.gal[i]) return T2N_E_BADARG;
         }
         b.weight = out->weight; b.ray_flags = scratch->ray_flags; b.g_rgb = g_rgb_map;
+        b.act_h1 = scratch->act_h1; b.act_h2 = scratch->act_h2; b.act_rows = scratch->act_rows;   // NULL -> recompute
         b.g_basis = grads->basis; b.g_w1p = scratch->w1_grad_packed; b.g_b1 = grads->b1; b.g_w2 = grads->w2;
         b.g_b2 = grads->b2; b.g_w3 = grads->w3; b.g_b3 = grads->b3;
         if (!grads->basis) return T2N_E_BADARG;
@@ -343,6 +345,11 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
             rc = launch_pack_w1(params->w1, params->col_perm, field->feature_c, field->mlp_in, field->mlp_in_pad,
                                 scratch->w1_packed, st);
             if (rc) return rc;
+        }
+        if (getenv("T2N_BWD_TRACE")) {
+            if (!g_trace) cudaMalloc(&g_trace, 32 * sizeof(long long));
+            cudaMemsetAsync(g_trace, 0, 32 * sizeof(long long), st);
+            b.trace = g_trace;
         }
         const AppBwdSmem BL = app_bwd_smem_layout(b.fw.n_app_total, b.fw.app_dim, b.fw.C, b.fw.Kp);
         const int smem = BL.total * 4;

@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             if (j - 2 >= 0 && j - 2 < n_tiles) {
                 cur_stage = 0;
                 acc_wait(1, j - 2);
+                const int e_row = (blockIdx.x + (j - 2) * gridDim.x) * kMmaM + erow;
                 for (int c = 0; c < nk2; ++c, ++it) {
                     uint32_t v[8];
                     const int col0 = c * 32 + eq * 8;
@@ -441,6 +442,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                     float h[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) h[q] = fmaxf(__uint_as_float(v[q]) + b1s[col0 + q], 0.f);
+                    if (args.act_h1 != nullptr && e_row < total && e_row < args.act_rows) {
+                        float4* dst = reinterpret_cast<float4*>(args.act_h1 + (size_t)e_row * 128 + col0);
+                        dst[0] = make_float4(h[0], h[1], h[2], h[3]);
+                        dst[1] = make_float4(h[4], h[5], h[6], h[7]);
+                    }
                     stage_acquire(it);
                     st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it & 1), eq * 8, h);
                     stage_publish_tmem(it);
@@ -592,12 +598,19 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                         uint32_t v[16];
                         const int col0 = eq * 32 + blk * 16;
                         tmem_ld16(tmem + tmem_lane + kColD2 + col0, v);
+                        float hv[16];
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
                             const float h = fmaxf(__uint_as_float(v[q]) + b2s[col0 + q], 0.f);
+                            hv[q] = h;
                             s0 = fmaf(h, w3s[col0 + q], s0);
                             s1 = fmaf(h, w3s[128 + col0 + q], s1);
                             s2 = fmaf(h, w3s[256 + col0 + q], s2);
+                        }
+                        if (args.act_h2 != nullptr && e0 + erow < total && e0 + erow < args.act_rows) {
+                            float4* dst = reinterpret_cast<float4*>(args.act_h2 + (size_t)(e0 + erow) * 128 + col0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dst[q] = make_float4(hv[4 * q], hv[4 * q + 1], hv[4 * q + 2], hv[4 * q + 3]);
                         }
                     }
                     float* pp = part + (erow * 4 + eq) * 4;

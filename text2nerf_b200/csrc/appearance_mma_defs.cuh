@@ -139,6 +139,9 @@ struct AppMmaArgs {
     unsigned char ident_src[32];
     unsigned char pe_src[32];
     unsigned char pe_nf[32];
+    float* act_h1;          // [A][128] relu(D1 + b1) per listed sample (NULL = do not save)
+    float* act_h2;          // [A][128] relu(D2 + b2)
+    long long act_rows;     // capacity of the two arrays in rows
     long long* trace;       // debug: 32 cycle counters written by CTA 0 (NULL = off), see t2n_debug_trace_read
 };
 

@@ -228,6 +228,10 @@ struct AppBwdArgs {
     float* g_b2;
     float* g_w3;
     float* g_b3;
+    const float* act_h1;        // [A][128] saved relu(layer 1) / relu(layer 2) of the forward, or NULL
+    const float* act_h2;
+    long long act_rows;
+    long long* trace;           // debug cycle counters of CTA 0 (NULL = off)
 };
 
 struct AppBwdSmem {
@@ -251,7 +255,9 @@ __host__ __device__ inline AppBwdSmem app_bwd_smem_layout(int n_app_total, int a
     return B;
 }
 
-constexpr int kMaxBasisPerThread = 21;      // ceil(27*192/256)
+constexpr int kBasisTilesPerThread = 2;     // 4x4 tiles of dBasis per thread: ceil(8 * 48 / 256)
+constexpr int kMaxBasisPerThread = 16 * kBasisTilesPerThread;
+constexpr int kMaxProdGroups = 12;          // float4 groups of dprod per thread: ceil(48 / 4)
 
 template <int NQ>
 __device__ __forceinline__ void app_scatter(const AppBwdArgs& b, const Axis ax[3], int c4, const float* dprod_row) {
@@ -325,6 +331,11 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
     const int zero_idx = a.app_dim + 6;
     const int* pairs = reinterpret_cast<const int*>(sm + L.pairs);
 
+    const bool tr = b.trace != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+    auto mark = [&](int ph) { const long long t = clock64(); tph[ph] += t - tlast; tlast = t; };
+    int ntile = 0;
     // thread-owned accumulators, flushed once at the end
     float gB[kMaxBasisPerThread];
 #pragma unroll
@@ -334,6 +345,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
     for (int tile = blockIdx.x; tile * kTM < total; tile += gridDim.x) {
         const int e0 = tile * kTM;
         // ---------------- G: gather products (kept for the basis gradient) + base extras
+        ++ntile; mark(11);
         {
             const int m = warp * 8 + grp;
             const int e = e0 + m;
@@ -385,6 +397,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
         __syncthreads();
 
         // per-point upstream gradient dL/drgb = w * G(ray)
+        mark(0);    // gather + basis
         float dc_mine = 0.f;            // for threads tid < 3*TM: (m = tid & 63, c = tid / 64)
         if (tid < kTM * 3) {
             const int m = tid & (kTM - 1), c = tid / kTM;
@@ -420,13 +433,29 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
             }
             __syncthreads();
         } else {
+            const bool saved = b.act_h1 != nullptr && b.act_h2 != nullptr && C == 128 && (long long)total <= b.act_rows;
+            const int nk1 = a.Kp / kKC;
+            if (saved) {
+                // ---------------- hidden activations saved by the tensor-core forward: load the tile
+                for (int idx = tid; idx < kTM * 32; idx += 256) {
+                    const int m = idx >> 5, q4 = idx & 31;
+                    const int e = e0 + m;
+                    float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1;
+                    if (e < total) {
+                        v1 = ldg4(b.act_h1 + (size_t)e * 128 + q4 * 4);
+                        v2 = ldg4(b.act_h2 + (size_t)e * 128 + q4 * 4);
+                    }
+                    *reinterpret_cast<float4*>(sm + L.h1 + m * hs + q4 * 4) = v1;
+                    *reinterpret_cast<float4*>(sm + L.h2 + m * hs + q4 * 4) = v2;
+                }
+                __syncthreads();
+            } else {
             // ---------------- decoder forward (same as app_forward_kernel)
             float acc[4][NJ];
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) acc[ii][jj] = 0.f;
-            const int nk1 = a.Kp / kKC;
             load_w_chunk(sm + L.b_chunk, a.w1p, C, a.Kp, 0);
             cp_async_commit();
             for (int kc = 0; kc < nk1; ++kc) {
@@ -478,7 +507,9 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                     if (n < C) sm[L.h2 + (ti + 16 * ii) * hs + n] = fmaxf(acc[ii][jj] + sm[L.b2 + n], 0.f);
                 }
             __syncthreads();
+            }
             // ---------------- layer 3 forward + sigmoid backward: dz3 = dc * c (1-c)
+            mark(1);    // decoder forward recompute (layers 1, 2)
             if (tid < kTM * 3) {
                 const int m = tid & (kTM - 1), c = tid / kTM;
                 const float* hrow = sm + L.h2 + m * hs;
@@ -486,7 +517,8 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                 float s = 0.f;
                 for (int k = 0; k < C; k += 4) s += f4_dot(lds4(hrow + k), lds4(wrow + k));
                 s += sm[L.b3 + c];
-                const float y = 1.f / (1.f + expf(-s));
+                float y = 1.f / (1.f + expf(-s));
+                if (saved && e0 + m < total) y = __ldg(a.app_rgb + (size_t)(e0 + m) * 3 + c);   // the forward's own output
                 sm[BL.dz3 + m * 4 + c] = dc_mine * y * (1.f - y);
             }
             __syncthreads();
@@ -517,6 +549,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                 sm[L.h2 + m * hs + k] = h > 0.f ? g : 0.f;
             }
             __syncthreads();
+            mark(2);    // layer 3 fwd/bwd, dW3, dz2
             // dW2[n][k] += sum_m dz2[m][n] h1[m][k]   8x8 register tile, vector red to global
             if (ti * 8 < C && tj * 8 < C) {
                 float o[8][8];
@@ -542,6 +575,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                     red_add_v4(dst + 4, make_float4(o[i][4], o[i][5], o[i][6], o[i][7]));
                 }
             }
+            mark(3);    // dW2 (+ global red)
             if (tid < C) {
                 float s = 0.f;
                 for (int m = 0; m < kTM; ++m) s += sm[L.h2 + m * hs + tid];
@@ -599,6 +633,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                 }
             }
             __syncthreads();
+            mark(4);    // dh1 -> dz1
             if (tid < C) {
                 float s = 0.f;
                 for (int m = 0; m < kTM; ++m) s += sm[L.h1 + m * hs + tid];
@@ -626,6 +661,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                     cp_async_wait<0>();
                     __syncthreads();
                     // dW1p[n][k] += sum_m dz1[m][n] A[m][k]
+                    mark(5);    // layer-1 backward: chunk load + column generation
                     if (ni * 4 < C) {
                         float o[4][4];
 #pragma unroll
@@ -649,6 +685,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                             red_add_v4(b.g_w1p + (size_t)(ni * 4 + i) * a.Kp + kc * kKC + kj * 4,
                                        make_float4(o[i][0], o[i][1], o[i][2], o[i][3]));
                     }
+                    mark(6);    // dW1 tile + global red
                     // dA[m][k] = sum_n dz1[m][n] W1p[n][k]  -> back through the column recipe
                     {
                         float o[2][4];
@@ -693,37 +730,70 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
                             }
                         }
                     }
+                    mark(7);    // dA tile + PE backward
                 }
             }
             __syncthreads();
         }
 
         // ---------------- basis backward
-        // dBasis[n][comp] += sum_m dfeat[m][n] prod[m][comp]   (thread-owned registers)
+        // dBasis[n][comp] += sum_m dfeat[m][n] prod[m][comp]: 4 x 4 register tiles, thread-owned across tiles
         {
-            const int nout = a.app_dim * NA;
+            const int ncb = NA >> 2;                                   // comp blocks of 4
+            const int ntile = ((a.app_dim + 3) >> 2) * ncb;
 #pragma unroll
-            for (int i = 0; i < kMaxBasisPerThread; ++i) {
-                const int idx = tid + i * 256;
-                if (idx < nout) {
-                    const int n = idx / NA, comp = idx - n * NA;
-                    float s = 0.f;
-                    for (int m = 0; m < kTM; ++m)
-                        s = fmaf(sm[BL.dbase + m * L.base_stride + n], sm[BL.prod + m * L.prod_stride + comp], s);
-                    gB[i] += s;
+            for (int rep = 0; rep < kBasisTilesPerThread; ++rep) {
+                const int t = tid + rep * 256;
+                if (t < ntile) {
+                    const int nb = t / ncb, cb = t - nb * ncb;
+                    float o[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+                    for (int m = 0; m < kTM; ++m) {
+                        const float* dr = sm + BL.dbase + m * L.base_stride + nb * 4;
+                        const float4 pv = lds4(sm + BL.prod + m * L.prod_stride + cb * 4);
+                        const float d[4] = {dr[0], dr[1], dr[2], dr[3]};       // rows beyond app_dim hold zeros / extras with zero grad
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            o[i][0] = fmaf(d[i], pv.x, o[i][0]); o[i][1] = fmaf(d[i], pv.y, o[i][1]);
+                            o[i][2] = fmaf(d[i], pv.z, o[i][2]); o[i][3] = fmaf(d[i], pv.w, o[i][3]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) gB[rep * 16 + i * 4 + j] += o[i][j];
                 }
             }
         }
         __syncthreads();
-        // dprod[m][comp] = sum_n dfeat[m][n] B[n][comp], in place over prod
-        for (int idx = tid; idx < kTM * NA; idx += 256) {
-            const int m = idx / NA, comp = idx - m * NA;
+        // dprod[m][comp] = sum_n dfeat[m][n] B[n][comp], in place over prod: thread = (point, every 4th float4 group)
+        {
+            const int m = tid & (kTM - 1), part = tid / kTM;
+            const int ngrp = NA >> 2;
+            float4 accp[kMaxProdGroups];
+#pragma unroll
+            for (int j = 0; j < kMaxProdGroups; ++j) accp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* drow = sm + BL.dbase + m * L.base_stride;
-            float s = 0.f;
-            for (int n = 0; n < a.app_dim; ++n) s = fmaf(drow[n], sm[L.basis + n * NA + comp], s);
-            sm[BL.prod + m * L.prod_stride + comp] = s;
+            for (int n = 0; n < a.app_dim; ++n) {
+                const float d = drow[n];
+                const float* brow = sm + L.basis + n * NA;
+#pragma unroll
+                for (int j = 0; j < kMaxProdGroups; ++j) {
+                    const int gq = part + 4 * j;
+                    if (gq < ngrp) accp[j] = f4_fma(d, lds4(brow + gq * 4), accp[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kMaxProdGroups; ++j) {
+                const int gq = part + 4 * j;
+                if (gq < ngrp) *reinterpret_cast<float4*>(sm + BL.prod + m * L.prod_stride + gq * 4) = accp[j];
+            }
         }
         __syncthreads();
+        mark(8);    // basis backward (dBasis, dprod)
         // ---------------- scatter into the app planes / lines
         {
             const int m = warp * 8 + grp;
@@ -746,15 +816,31 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
             }
         }
         __syncthreads();
+        mark(9);    // scatter into app planes / lines
     }
 
+    if (tr) {
+        for (int q = 0; q < 12; ++q) b.trace[q] = tph[q];
+        b.trace[12] = ntile;
+    }
     // ---------------- flush thread-owned accumulators
     {
-        const int nout = a.app_dim * NA;
+        const int ncb = NA >> 2;
+        const int ntile = ((a.app_dim + 3) >> 2) * ncb;
 #pragma unroll
-        for (int i = 0; i < kMaxBasisPerThread; ++i) {
-            const int idx = tid + i * 256;
-            if (idx < nout && gB[i] != 0.f) atomicAdd(b.g_basis + idx, gB[i]);
+        for (int rep = 0; rep < kBasisTilesPerThread; ++rep) {
+            const int t = tid + rep * 256;
+            if (t < ntile) {
+                const int nb = t / ncb, cb = t - nb * ncb;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = nb * 4 + i;
+                        const float v = gB[rep * 16 + i * 4 + j];
+                        if (n < a.app_dim && v != 0.f) atomicAdd(b.g_basis + n * NA + cb * 4 + j, v);
+                    }
+            }
         }
         if (mlp) {
             if (tid < 3 * C && gW3a != 0.f) atomicAdd(b.g_w3 + tid, gW3a);

@@ -73,7 +73,7 @@ def sharded_train_step(model, optimizer, rays, targets_fn, n_samples, rank: int,
     jitter_full = torch.rand(R, 1)                      # same CPU draw on every rank (tensorBase.py:316)
     from .tensorBase import _RenderFn
     out = _RenderFn.apply(model, rays[lo:hi].contiguous(), jitter_full[lo:hi].to(rays.device).view(-1).contiguous(),
-                          n_samples, True, bool(white_bg), *model._flat_params())
+                          n_samples, True, bool(white_bg), True, *model._flat_params())
     loss = targets_fn(lo, hi, out) * world               # undo the 1/world of the all-reduce average
     loss.backward()
     allreduce_flat_grads(model, world)

@@ -229,11 +229,13 @@ class _RenderFn(torch.autograd.Function):
     t2n_render_backward."""
 
     @staticmethod
-    def forward(ctx, model, rays, jitter, n_samples, is_train, white_bg, *params):
+    def forward(ctx, model, rays, jitter, n_samples, is_train, white_bg, track_grad, *params):
         lib = nat.load()
         dev = rays.device
         R, S = rays.shape[0], n_samples
-        need_bwd = any(ctx.needs_input_grad[6:])      # grad mode is off inside Function.forward
+        # grad mode is always off inside Function.forward and needs_input_grad ignores no_grad(): the caller
+        # passes torch.is_grad_enabled() explicitly
+        need_bwd = bool(track_grad) and any(ctx.needs_input_grad[7:])
         p_cl = model._native_param_tensors(params)
         field = model._native_field()
         pstruct = model._native_params(p_cl)
@@ -253,11 +255,17 @@ class _RenderFn(torch.autograd.Function):
             w1_packed=model._w1_packed_buffer(dev),
             ray_flags=torch.empty((R,), **i32),
             w1_grad_packed=None,
-            mma_pack=model._mma_pack_buffer(dev, field))
+            mma_pack=model._mma_pack_buffer(dev, field), act_h1=None, act_h2=None, act_rows=0)
+        if need_bwd and sc["mma_pack"] is not None and int(field.feature_c) == 128:
+            # hidden activations of the decoder for the backward: capacity min(R*S, 8 Mi rows = 4 GiB each);
+            # only listed samples are touched, and a batch that lists more makes the backward recompute
+            sc["act_rows"] = min(R * S, 1 << 23)
+            sc["act_h1"] = torch.empty((sc["act_rows"], 128), **f32)
+            sc["act_h2"] = torch.empty((sc["act_rows"], 128), **f32)
         mask = model.alphaMask.native() if model.alphaMask is not None else None
         batch = nat.T2NBatch(_ptr(rays), _ptr(jitter), R, S, int(is_train), int(white_bg))
         outs = nat.T2NOutputs(_ptr(rgb_map), _ptr(depth_map), _ptr(z_vals), _ptr(weight))
-        scratch = nat.T2NScratch(*[_ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
+        scratch = nat.T2NScratch(*[sc[k] if k == "act_rows" else _ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = lib.t2n_render_forward(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
@@ -294,7 +302,7 @@ class _RenderFn(torch.autograd.Function):
         mask = model.alphaMask.native() if model.alphaMask is not None else None
         batch = nat.T2NBatch(_ptr(rays), _ptr(jitter) if jitter.numel() else None, R, S, int(is_train), int(white_bg))
         outs = nat.T2NOutputs(_ptr(rgb_map), None, _ptr(z_vals), _ptr(weight))
-        scratch = nat.T2NScratch(*[_ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
+        scratch = nat.T2NScratch(*[sc[k] if k == "act_rows" else _ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = lib.t2n_render_backward(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
@@ -302,7 +310,7 @@ class _RenderFn(torch.autograd.Function):
                                          _ptr(g_w), C.byref(gstruct), stream)
         nat.check(rc, "t2n_render_backward")
         ctx.scratch = None
-        return (None, None, None, None, None, None, *model._grads_for_autograd(grads))
+        return (None, None, None, None, None, None, None, *model._grads_for_autograd(grads))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -571,12 +579,12 @@ class TensorBase(torch.nn.Module):
         params = self._flat_params()
         max_rays = max(1, ((1 << 31) - 1) // S)
         if R <= max_rays:
-            return _RenderFn.apply(self, rays, jitter, S, bool(is_train), white, *params)
+            return _RenderFn.apply(self, rays, jitter, S, bool(is_train), white, torch.is_grad_enabled(), *params)
         outs = [[], [], [], []]
         for s in range(0, R, max_rays):
             part = _RenderFn.apply(self, rays[s:s + max_rays].contiguous(),
                                    None if jitter is None else jitter[s:s + max_rays].contiguous(),
-                                   S, bool(is_train), white, *params)
+                                   S, bool(is_train), white, torch.is_grad_enabled(), *params)
             for lst, t in zip(outs, part):
                 lst.append(t)
         return tuple(torch.cat(x) for x in outs)

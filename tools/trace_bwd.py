@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Cycle-counter trace of app_backward_kernel (CTA 0) on one 4096-ray training batch of the bench workload."""
+import contextlib
+import ctypes as C
+import io
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["T2N_BWD_TRACE"] = "1"
+import bench  # noqa: E402
+from oracle import t2n_oracle as orc  # noqa: E402
+from text2nerf_b200 import TensorVMSplit, _native as nat, ray_utils  # noqa: E402
+
+dev = torch.device("cuda:0")
+spec = bench.make_spec()
+params = bench.make_params(spec)
+S = orc.derive_step(spec)[1]
+with contextlib.redirect_stdout(io.StringIO()):
+    model = TensorVMSplit(spec.aabb_t().to(dev), bench.GRID, dev, density_n_comp=[16, 16, 16], appearance_n_comp=[48, 48, 48],
+                          app_dim=27, near_far=bench.NEAR_FAR, shadingMode="MLP_Fea_noview", step_ratio=bench.STEP_RATIO,
+                          fea_pe=6, view_pe=2)
+model.load_state_dict({k: v.to(dev) for k, v in params.items()})
+rays = ray_utils.camera_rays(bench.view_pose(0), bench.H, bench.W, [bench.FOCAL] * 2, device=dev)
+g = torch.Generator().manual_seed(0)
+for _ in range(2):
+    idx = torch.randint(0, rays.shape[0], (4096,), generator=g).to(dev)
+    out = model(rays[idx].contiguous(), is_train=True, white_bg=True, N_samples=S)
+    orc.training_loss(*out, torch.rand(4096, 3, generator=g).to(dev), (2 + 4 * torch.rand(4096, generator=g)).to(dev)).backward()
+torch.cuda.synchronize()
+buf = (C.c_longlong * 32)()
+nat.load().t2n_debug_trace_read(buf)
+v = list(buf)
+nt = max(v[12], 1)
+names = ["gather+basis", "decoder fwd recompute", "L3 fwd/bwd,dW3,dz2", "dW2+red", "dh1->dz1", "L1bwd: load+columns", "dW1+red",
+         "dA+PE bwd", "basis bwd", "scatter", "-", "loop overhead"]
+print("tiles of CTA0:", v[12], " total cycles/tile:", sum(v[:12]) / nt)
+for n, c in zip(names, v[:12]):
+    print(f"  {n:24s} {c / nt:10.0f} cyc/tile  {100 * c / max(sum(v[:12]), 1):5.1f}%")
