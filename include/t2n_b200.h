@@ -32,7 +32,7 @@ extern "C" {
 
 typedef struct CUstream_st* t2n_stream_t;   /* == cudaStream_t */
 
-#define T2N_ABI_VERSION 7
+#define T2N_ABI_VERSION 8
 
 enum {
     T2N_E_BADARG   = -1,   /* null pointer / non-positive size */
@@ -154,10 +154,15 @@ typedef struct T2NOutputs {
  *   mma_pack   t2n_mma_pack_floats(field) float              pre-swizzled hi/lo TF32 operand images of
  *                                                            basis_mat, w1 and w2 for the tensor-core
  *                                                            decoder (NULL selects the FFMA decoder)
- *   act_h1, act_h2  128*act_rows float each (optional, training) hidden activations relu(.) of the decoder per
- *                                                            listed sample, written by the tensor-core forward so
- *                                                            the backward does not recompute layers 1-2; when more
- *                                                            than act_rows samples are listed the backward recomputes
+ *   act_rows   capacity, in listed samples (multiple of 128), of the training-state arrays below; a batch that
+ *              lists more samples than act_rows falls back to the recomputing FFMA backward (correct, slower)
+ *   act_h1_img, act_h2_img  1024*act_rows bytes each (optional, training): hidden activations relu(.) of the
+ *              decoder per listed sample, written by the tensor-core forward as TF32 hi/lo MN-major operand images
+ *              (csrc/operand_image.cuh) -- they are the B / A operands of the dW2 / dW3 GEMMs of the backward
+ *   act_feat   32*act_rows float (optional, training): appearance feature (basis output) per listed sample
+ *   bwd_pack   t2n_bwd_pack_floats(field) float (backward only): transposed hi/lo weight images of W2, W1, basis
+ *   bwd_img    t2n_bwd_image_row_bytes(field)*act_rows bytes (backward only): operand images the backward-data
+ *              kernel writes for the weight-gradient GEMMs (dz2, dz1, decoder columns, dfeat, products, dz3)
  * A batch with R*S >= 2^31 is rejected with T2N_E_CAPACITY. */
 typedef struct T2NScratch {
     float*   sigma_feat;
@@ -173,9 +178,12 @@ typedef struct T2NScratch {
     int32_t* ray_flags;
     float*   w1_grad_packed;
     float*   mma_pack;
-    float*   act_h1;
-    float*   act_h2;
+    uint8_t* act_h1_img;
+    uint8_t* act_h2_img;
+    float*   act_feat;
     int64_t  act_rows;
+    float*   bwd_pack;
+    uint8_t* bwd_img;
 } T2NScratch;
 
 /* ---- entry points ------------------------------------------------------------------------ */
@@ -187,6 +195,11 @@ const char* t2n_error_string(int code);
  * is outside its shape envelope (MLP heads, feature_c == 128, app_dim <= 32, every n_app a multiple
  * of 16, sum(n_app) <= 160) -- then the exact FFMA decoder is the only path. */
 size_t t2n_mma_pack_floats(const T2NField* field);
+
+/* Sizes of the tensor-core backward's scratch (T2NScratch.bwd_pack in floats, T2NScratch.bwd_img in bytes per
+ * row of act_rows); 0 when the field is outside the tensor-core envelope (same rule as t2n_mma_pack_floats). */
+size_t t2n_bwd_pack_floats(const T2NField* field);
+size_t t2n_bwd_image_row_bytes(const T2NField* field);
 
 /* Number of SMs / device check for the current device (0 on failure). */
 int t2n_device_sm_count(void);
@@ -225,13 +238,22 @@ int t2n_compute_alpha(const T2NField* field, const T2NParams* params, const T2NA
 /* Measurement aid (bench.py roofline leg; not part of the reference surface).  While enabled,
  * every forward/backward call records CUDA events on its stream around each kernel it launches.
  * t2n_profile_read synchronises on the last event and writes up to n (kernel id, milliseconds)
- * pairs of the most recent call: ids 0=march 1=pack_w1 2=appearance 3=finalize 4=app_backward
- * 5=unpack_w1_grad 6=ray_backward.  Returns the number of pairs written. */
+ * pairs of the most recent call: ids 0=march 1=pack_w1 2=appearance 3=finalize 4=app_backward (FFMA fallback)
+ * 5=unpack_w1_grad 6=ray_backward 7=pack_bwd 8=app_backward_mma 9=wgrad (four launches).  Returns the number
+ * of pairs written. */
 int t2n_profile_enable(int on);
 /* Debug aid: with T2N_MMA_TRACE set in the environment the tensor-core appearance kernel's CTA 0 writes
  * 32 cycle counters (stage times, barrier waits); this copies them to the host.  Returns 32 or 0. */
 int t2n_debug_trace_read(long long* out32);
 int t2n_profile_read(int* ids, float* ms, int n);
+
+/* Test aids for the weight-gradient GEMM kernel (csrc/wgrad_mma.cuh), not part of the reference surface.
+ * t2n_debug_make_image: dense rows [n_rows][32*n_groups] fp32 -> operand image (img_bytes(n_rows, n_groups) =
+ * ceil(n_rows/128) * 32768 * n_groups bytes).  t2n_debug_wgrad: out[128][32*ngy] += X^T Y over n_rows samples
+ * (n_rows is read from count_dev[0]); ones_out[128] += column sums of X (may be NULL); ngx is 4 or 1. */
+int t2n_debug_make_image(const float* rows, int n_rows, int n_groups, uint8_t* img, t2n_stream_t stream);
+int t2n_debug_wgrad(const uint8_t* x_img, int ngx, const uint8_t* y_img, int ngy, const int32_t* count_dev,
+                    long long cap_rows, float* out, float* ones_out, t2n_stream_t stream);
 
 #ifdef __cplusplus
 }

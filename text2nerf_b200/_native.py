@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libt2n_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class NativeLibraryError(RuntimeError):
@@ -77,8 +77,8 @@ class T2NScratch(C.Structure):
                 ("dsum", C.c_void_p), ("ray_start", C.c_void_p), ("ray_count", C.c_void_p),
                 ("slots", C.c_void_p), ("app_rgb", C.c_void_p), ("counters", C.c_void_p),
                 ("w1_packed", C.c_void_p), ("ray_flags", C.c_void_p), ("w1_grad_packed", C.c_void_p),
-                ("mma_pack", C.c_void_p), ("act_h1", C.c_void_p), ("act_h2", C.c_void_p),
-                ("act_rows", C.c_int64)]
+                ("mma_pack", C.c_void_p), ("act_h1_img", C.c_void_p), ("act_h2_img", C.c_void_p),
+                ("act_feat", C.c_void_p), ("act_rows", C.c_int64), ("bwd_pack", C.c_void_p), ("bwd_img", C.c_void_p)]
 
 
 # every symbol include/t2n_b200.h declares, with its ctypes signature
@@ -87,6 +87,11 @@ SYMBOLS = {
     "t2n_error_string": (C.c_char_p, [C.c_int]),
     "t2n_device_sm_count": (C.c_int, []),
     "t2n_mma_pack_floats": (C.c_size_t, [C.POINTER(T2NField)]),
+    "t2n_bwd_pack_floats": (C.c_size_t, [C.POINTER(T2NField)]),
+    "t2n_bwd_image_row_bytes": (C.c_size_t, [C.POINTER(T2NField)]),
+    "t2n_debug_make_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "t2n_debug_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "t2n_render_forward": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
                                      C.POINTER(T2NBatch), C.POINTER(T2NOutputs), C.POINTER(T2NScratch),
                                      C.c_void_p]),
@@ -135,8 +140,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     return lib
 
 
-KERNEL_NAMES = {0: "march", 1: "pack_w1", 2: "appearance", 3: "finalize", 4: "app_backward",
-                5: "unpack_w1_grad", 6: "ray_backward"}
+KERNEL_NAMES = {0: "march", 1: "pack_w1", 2: "appearance", 3: "finalize", 4: "app_backward_ffma",
+                5: "unpack_w1_grad", 6: "ray_backward", 7: "pack_bwd", 8: "app_backward_mma", 9: "wgrad"}
 
 
 def profile_read():

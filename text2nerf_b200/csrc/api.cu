@@ -167,6 +167,18 @@ size_t t2n_mma_pack_floats(const T2NField* field) {
     return mma_pack_layout(field->n_app[0] + field->n_app[1] + field->n_app[2], R.Kp).total;
 }
 
+size_t t2n_bwd_pack_floats(const T2NField* field) {
+    MmaRecipe R;
+    if (!field || !mma_recipe(field, R)) return 0;
+    return bwd_pack_layout(field->n_app[0] + field->n_app[1] + field->n_app[2], R.Kp).total;
+}
+
+size_t t2n_bwd_image_row_bytes(const T2NField* field) {
+    MmaRecipe R;
+    if (!field || !mma_recipe(field, R)) return 0;
+    return bwd_img_row_bytes(field->n_app[0] + field->n_app[1] + field->n_app[2], R.Kp);
+}
+
 int t2n_profile_enable(int on) {
     g_prof.on = on != 0;
     g_prof.n = 0;
@@ -260,7 +272,10 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
             memset(&ma2, 0, sizeof(ma2));
             ma2.fw = aa;
             ma2.pack = scratch->mma_pack;
-            ma2.act_h1 = scratch->act_h1; ma2.act_h2 = scratch->act_h2; ma2.act_rows = scratch->act_rows;
+            if (scratch->act_h1_img && scratch->act_h2_img && scratch->act_feat && scratch->act_rows >= 128) {
+                ma2.h1_img = scratch->act_h1_img; ma2.h2_img = scratch->act_h2_img; ma2.feat = scratch->act_feat;
+                ma2.act_rows = scratch->act_rows & ~(int64_t)127;
+            }
             ma2.n_freq = R.n_freq; ma2.pe_chunks = R.pe_chunks; ma2.Kp = R.Kp;
             memcpy(ma2.ident_src, R.ident_src, 32); memcpy(ma2.pe_src, R.pe_src, 32); memcpy(ma2.pe_nf, R.pe_nf, 32);
             const char* tenv = getenv("T2N_MMA_TERMS");          // accuracy study hook; default 3xTF32
@@ -331,7 +346,8 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
             if (!b.gap[i] || !b.gal[i]) return T2N_E_BADARG;
         }
         b.weight = out->weight; b.ray_flags = scratch->ray_flags; b.g_rgb = g_rgb_map;
-        b.act_h1 = scratch->act_h1; b.act_h2 = scratch->act_h2; b.act_rows = scratch->act_rows;   // NULL -> recompute
+        b.act_h1 = nullptr; b.act_h2 = nullptr; b.act_rows = 0;       // the FFMA kernel recomputes the decoder
+        b.skip_if_le = -1;
         b.g_basis = grads->basis; b.g_w1p = scratch->w1_grad_packed; b.g_b1 = grads->b1; b.g_w2 = grads->w2;
         b.g_b2 = grads->b2; b.g_w3 = grads->w3; b.g_b3 = grads->b3;
         if (!grads->basis) return T2N_E_BADARG;
@@ -346,7 +362,98 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
                                 scratch->w1_packed, st);
             if (rc) return rc;
         }
-        if (getenv("T2N_BWD_TRACE")) {
+        g_prof.begin_call();
+        // ---- tensor-core path: backward-data kernel + four weight-gradient GEMMs over operand images
+        MmaRecipe R;
+        MmaBwdRecipe RB;
+        const int64_t cap_rows = scratch->act_rows & ~(int64_t)127;
+        const bool use_mma = mlp && scratch->act_h1_img && scratch->act_h2_img && scratch->act_feat && scratch->bwd_pack &&
+                             scratch->bwd_img && cap_rows >= 128 && !getenv("T2N_BWD_FFMA") && mma_recipe(field, R) &&
+                             build_mma_bwd_recipe(R, field->app_dim, RB);
+        if (use_mma) {
+            const int NA = b.fw.n_app_total;
+            const BwdPack P = bwd_pack_layout(NA, R.Kp);
+            const int ngc = P.w1_chunks, ngp = P.b_chunks;
+            if (!grads->w1 || !grads->b1 || !grads->w2 || !grads->b2 || !grads->w3 || !grads->b3) return T2N_E_BADARG;
+            BwdPackArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            pa.basis = params->basis; pa.w1 = params->w1; pa.w2 = params->w2;
+            pa.app_dim = field->app_dim; pa.n_app_total = NA; pa.K = field->mlp_in; pa.Kp = R.Kp;
+            memcpy(pa.own, RB.own, 32); memcpy(pa.perm, RB.perm, sizeof(pa.perm));
+            pa.out = scratch->bwd_pack;
+            g_prof.start(7, st);
+            rc = launch_pack_bwd(pa, st);
+            g_prof.stop(st);
+            if (rc) return rc;
+
+            uint8_t* img = scratch->bwd_img;
+            BwdMmaArgs d;
+            memset(&d, 0, sizeof(d));
+            d.fw = b.fw;
+            d.pack = scratch->bwd_pack;
+            const char* tenv = getenv("T2N_MMA_TERMS");
+            d.terms = tenv ? atoi(tenv) : 7;
+            d.n_freq = R.n_freq; d.pe_chunks = R.pe_chunks; d.Kp = R.Kp;
+            memcpy(d.own, RB.own, 32); memcpy(d.pe_nf, R.pe_nf, 32);
+            d.weight = out->weight; d.ray_flags = scratch->ray_flags; d.g_rgb = g_rgb_map;
+            d.h1_img = scratch->act_h1_img; d.h2_img = scratch->act_h2_img; d.feat = scratch->act_feat;
+            d.cap_rows = cap_rows;
+            d.dz2_img = img;  img += (size_t)cap_rows * 1024;
+            d.dz1_img = img;  img += (size_t)cap_rows * 1024;
+            d.cols_img = img; img += (size_t)cap_rows * 256 * ngc;
+            d.dfeat_img = img; img += (size_t)cap_rows * 256;
+            d.prod_img = img; img += (size_t)cap_rows * 256 * ngp;
+            d.dz3_img = img;
+            for (int i = 0; i < 3; ++i) { d.gap[i] = b.gap[i]; d.gal[i] = b.gal[i]; }
+            d.g_b3 = grads->b3;
+            if (getenv("T2N_BWD_TRACE")) {
+                if (!g_trace) cudaMalloc(&g_trace, 32 * sizeof(long long));
+                cudaMemsetAsync(g_trace, 0, 32 * sizeof(long long), st);
+                d.trace = g_trace;
+            }
+            const int smem_bd = bwd_smem_layout().total;
+            if (smem_bd > dev.max_smem_optin) return T2N_E_SHADING;
+            g_prof.start(8, st);
+            rc = launch_app_backward_mma(d, smem_bd, dev.sm_count, st);
+            g_prof.stop(st);
+            if (rc) return rc;
+
+            WgradArgs w;
+            auto base = [&](const uint8_t* x, int ngx, const uint8_t* y, int ngy, float* o, float* ones) {
+                memset(&w, 0, sizeof(w));
+                w.x_img = x; w.ngx = ngx; w.y_img = y; w.ngy = ngy; w.counters = scratch->counters; w.cap_rows = cap_rows;
+                w.terms = d.terms; w.out = o; w.ones_out = ones;
+                for (int i = 0; i < 128; ++i) { w.row_off[i] = -1; w.row_off_ones[i] = -1; }
+                for (int i = 0; i < kMaxYGroups * 32; ++i) w.col_off[i] = -1;
+            };
+            g_prof.start(9, st);
+            // dW2[n][k] = sum dz2[m][n] h1[m][k], db2
+            base(d.dz2_img, 4, d.h1_img, 4, grads->w2, grads->b2);
+            for (int n = 0; n < 128; ++n) { w.row_off[n] = n * 128; w.row_off_ones[n] = n; w.col_off[n] = n; }
+            rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
+            if (rc) return rc;
+            // dW1[n][perm[k]] = sum dz1[m][n] cols[m][k], db1
+            base(d.dz1_img, 4, d.cols_img, ngc, grads->w1, grads->b1);
+            for (int n = 0; n < 128; ++n) { w.row_off[n] = n * field->mlp_in; w.row_off_ones[n] = n; }
+            for (int k = 0; k < 32 * ngc; ++k) w.col_off[k] = RB.perm[k];
+            rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
+            if (rc) return rc;
+            // dBasis[own[s]][comp] = sum dfeat[m][s] prod[m][comp]
+            base(d.dfeat_img, 1, d.prod_img, ngp, grads->basis, nullptr);
+            for (int s = 0; s < 32; ++s) w.row_off[s] = RB.own[s] < field->app_dim ? RB.own[s] * NA : -1;
+            for (int c = 0; c < NA; ++c) w.col_off[c] = c;
+            rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
+            if (rc) return rc;
+            // dW3[c][n] = sum h2[m][n] dz3[m][c]
+            base(d.h2_img, 4, d.dz3_img, 1, grads->w3, nullptr);
+            for (int n = 0; n < 128; ++n) w.row_off[n] = n;
+            for (int c = 0; c < 3; ++c) w.col_off[c] = c * 128;
+            rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
+            g_prof.stop(st);
+            if (rc) return rc;
+            b.skip_if_le = cap_rows;        // the FFMA kernel below only runs when the list overflowed the images
+        }
+        if (!use_mma && getenv("T2N_BWD_TRACE")) {
             if (!g_trace) cudaMalloc(&g_trace, 32 * sizeof(long long));
             cudaMemsetAsync(g_trace, 0, 32 * sizeof(long long), st);
             b.trace = g_trace;
@@ -354,7 +461,6 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
         const AppBwdSmem BL = app_bwd_smem_layout(b.fw.n_app_total, b.fw.app_dim, b.fw.C, b.fw.Kp);
         const int smem = BL.total * 4;
         if (smem > dev.max_smem_optin) return T2N_E_SHADING;
-        g_prof.begin_call();
         g_prof.start(4, st);
         rc = launch_app_backward(b, max_quads(field->n_app), smem, dev.sm_count, st);
         g_prof.stop(st);
@@ -394,6 +500,26 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
         g_prof.stop(st);
     }
     return rc;
+}
+
+int t2n_debug_make_image(const float* rows, int n_rows, int n_groups, uint8_t* img, t2n_stream_t stream) {
+    if (!rows || !img || n_rows <= 0 || n_groups <= 0) return T2N_E_BADARG;
+    return launch_make_image(rows, n_rows, n_groups, img, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2n_debug_wgrad(const uint8_t* x_img, int ngx, const uint8_t* y_img, int ngy, const int32_t* count_dev,
+                    long long cap_rows, float* out, float* ones_out, t2n_stream_t stream) {
+    if (!x_img || !y_img || !count_dev || !out || (ngx != 1 && ngx != 4) || ngy < 1 || ngy > kMaxYGroups) return T2N_E_BADARG;
+    DeviceInfo& dev = device_info();
+    if (!dev.ok || dev.cc_major != 10) return T2N_E_DEVICE;
+    WgradArgs w;
+    memset(&w, 0, sizeof(w));
+    w.x_img = x_img; w.ngx = ngx; w.y_img = y_img; w.ngy = ngy; w.counters = count_dev; w.cap_rows = cap_rows;
+    w.terms = 7; w.out = out; w.ones_out = ones_out;
+    const int ld = 32 * ngy;
+    for (int i = 0; i < 128; ++i) { w.row_off[i] = (ngx == 4 || i < 32) ? i * ld : -1; w.row_off_ones[i] = (ngx == 4 || i < 32) ? i : -1; }
+    for (int i = 0; i < kMaxYGroups * 32; ++i) w.col_off[i] = i < ld ? i : -1;
+    return launch_wgrad(w, dev.max_smem_optin, dev.sm_count, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int t2n_get_rays(const float* c2w_host, float fx, float fy, float cx, float cy, int H, int W,

@@ -139,9 +139,10 @@ struct AppMmaArgs {
     unsigned char ident_src[32];
     unsigned char pe_src[32];
     unsigned char pe_nf[32];
-    float* act_h1;          // [A][128] relu(D1 + b1) per listed sample (NULL = do not save)
-    float* act_h2;          // [A][128] relu(D2 + b2)
-    long long act_rows;     // capacity of the two arrays in rows
+    uint8_t* h1_img;        // relu(D1 + b1) per listed sample as a 4-group MN-major operand image (wgrad_mma.cuh); NULL = do not save
+    uint8_t* h2_img;        // relu(D2 + b2), same format
+    float* feat;            // [rows][32] appearance feature (basis output), zero padded
+    long long act_rows;     // capacity of the three arrays in rows (multiple of 128)
     long long* trace;       // debug: 32 cycle counters written by CTA 0 (NULL = off), see t2n_debug_trace_read
 };
 

@@ -231,6 +231,7 @@ struct AppBwdArgs {
     const float* act_h1;        // [A][128] saved relu(layer 1) / relu(layer 2) of the forward, or NULL
     const float* act_h2;
     long long act_rows;
+    long long skip_if_le;       // >= 0: do nothing when the list has <= this many samples (the tensor-core path ran)
     long long* trace;           // debug cycle counters of CTA 0 (NULL = off)
 };
 
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
     const AppSmem& L = BL.fw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = a.counters[0];
+    if (b.skip_if_le >= 0 && (long long)total <= b.skip_if_le) return;
     const int C = a.C;
     const int NA = a.n_app_total;
     const bool mlp = a.shading <= T2N_SHADE_MLP;

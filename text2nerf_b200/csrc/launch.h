@@ -5,6 +5,7 @@
 #include "appearance.cuh"
 #include "backward.cuh"
 #include "appearance_mma_defs.cuh"
+#include "bwd_mma_defs.cuh"
 
 
 namespace t2n {
@@ -17,4 +18,8 @@ int launch_pack_w1(const float* w1, const int32_t* perm, int C, int K, int Kp, f
 int launch_ray_backward(const RayBwdArgs& a, int nq, int smem_bytes, int grid, cudaStream_t st);
 int launch_app_backward(const AppBwdArgs& a, int nq, int smem_bytes, int grid, cudaStream_t st);
 int launch_unpack_w1_grad(const float* gw1p, const int32_t* perm, int C, int K, int Kp, float* gw1, cudaStream_t st);
+int launch_pack_bwd(const BwdPackArgs& a, cudaStream_t st);
+int launch_app_backward_mma(const BwdMmaArgs& a, int smem_bytes, int grid, cudaStream_t st);
+int launch_wgrad(WgradArgs& a, int max_smem, int grid, cudaStream_t st);
+int launch_make_image(const float* rows, int n_rows, int ng, uint8_t* img, cudaStream_t st);
 }  // namespace t2n

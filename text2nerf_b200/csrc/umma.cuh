@@ -1,0 +1,140 @@
+// tcgen05 / TMEM / mbarrier helpers shared by the tensor-core kernels (forward appearance, backward data,
+// weight gradients).  No kernels in this header: it may be included by several translation units.
+#pragma once
+#include "appearance_mma_defs.cuh"
+#include "operand_image.cuh"
+
+namespace t2n {
+
+// ---- tcgen05 / descriptor helpers ---------------------------------------------------------------
+// byte offset of 16-byte chunk j (0..7) of row r inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int j) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void st_split4(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, float4 v) {
+    uint4 h, l;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l.x = __float_as_uint(v.x - __uint_as_float(h.x));
+    l.y = __float_as_uint(v.y - __uint_as_float(h.y));
+    l.z = __float_as_uint(v.z - __uint_as_float(h.z));
+    l.w = __float_as_uint(v.w - __uint_as_float(h.w));
+    *reinterpret_cast<uint4*>(tile_hi + off) = h;
+    *reinterpret_cast<uint4*>(tile_lo + off) = l;
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                              // LBO (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // SBO [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// A operand from tensor memory (lane = row, column = k), B from shared memory: halves the shared-memory
+// operand traffic of the 3xTF32 decoder GEMMs, which otherwise bounds the kernel (12 MMAs x 8 KB per chunk)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// split 8 fp32 values into TF32 hi / lo and store them as columns [col, col+8) of a TMEM A stage (hi | lo)
+__device__ __forceinline__ void st_split8_tmem(uint32_t a_stage_lane, int col, const float (&v)[8]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        h[q] = tf32_hi(v[q]);
+        l[q] = __float_as_uint(v[q] - __uint_as_float(h[q]));
+    }
+    tmem_st8(a_stage_lane + col, h);
+    tmem_st8(a_stage_lane + 32 + col, l);
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// ---- warp-uniform issue path -----------------------------------------------------------------------
+// The issuer warp stays converged and every lane executes these; `elect.sync` picks the one lane that
+// actually issues.  With uniform control flow ptxas keeps descriptors in uniform registers and the
+// tensor pipe runs at its nominal 64 cycles per 128x128x8 TF32 MMA; issuing from a divergent
+// `if (lane == 0)` branch costs ~170 cycles per MMA (tools/mma_rate.cu, measured on B200).
+__device__ __forceinline__ void umma_ss_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        :: "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+        :: "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_elect(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+        :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar_addr) : "memory");
+}
+// low 32 bits of a SWIZZLE_128B K-major descriptor (start address | LBO); the high word is constant
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3fffu) | (1u << 16); }
+constexpr uint32_t kDescHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));   // SBO | version | SWIZZLE_128B
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int kProdWarps = 16;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kMmaThreads = kProdThreads + 32;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kProdThreads) : "memory"); }
+
+
+}  // namespace t2n

@@ -236,6 +236,8 @@ class _RenderFn(torch.autograd.Function):
         # grad mode is always off inside Function.forward and needs_input_grad ignores no_grad(): the caller
         # passes torch.is_grad_enabled() explicitly
         need_bwd = bool(track_grad) and any(ctx.needs_input_grad[7:])
+        if need_bwd:
+            model._poll_listed_count()
         p_cl = model._native_param_tensors(params)
         field = model._native_field()
         pstruct = model._native_params(p_cl)
@@ -255,13 +257,16 @@ class _RenderFn(torch.autograd.Function):
             w1_packed=model._w1_packed_buffer(dev),
             ray_flags=torch.empty((R,), **i32),
             w1_grad_packed=None,
-            mma_pack=model._mma_pack_buffer(dev, field), act_h1=None, act_h2=None, act_rows=0)
+            mma_pack=model._mma_pack_buffer(dev, field), act_h1_img=None, act_h2_img=None, act_feat=None,
+            act_rows=0, bwd_pack=None, bwd_img=None)
         if need_bwd and sc["mma_pack"] is not None and int(field.feature_c) == 128:
-            # hidden activations of the decoder for the backward: capacity min(R*S, 8 Mi rows = 4 GiB each);
-            # only listed samples are touched, and a batch that lists more makes the backward recompute
-            sc["act_rows"] = min(R * S, 1 << 23)
-            sc["act_h1"] = torch.empty((sc["act_rows"], 128), **f32)
-            sc["act_h2"] = torch.empty((sc["act_rows"], 128), **f32)
+            # training state of the tensor-core backward: decoder activations as operand images + features,
+            # sized from the running estimate of listed samples (a batch that overflows it takes the FFMA path)
+            rows = model._act_capacity(R, S)
+            sc["act_rows"] = rows
+            sc["act_h1_img"] = torch.empty((rows * 1024,), device=dev, dtype=torch.uint8)
+            sc["act_h2_img"] = torch.empty((rows * 1024,), device=dev, dtype=torch.uint8)
+            sc["act_feat"] = torch.empty((rows, 32), **f32)
         mask = model.alphaMask.native() if model.alphaMask is not None else None
         batch = nat.T2NBatch(_ptr(rays), _ptr(jitter), R, S, int(is_train), int(white_bg))
         outs = nat.T2NOutputs(_ptr(rgb_map), _ptr(depth_map), _ptr(z_vals), _ptr(weight))
@@ -272,6 +277,8 @@ class _RenderFn(torch.autograd.Function):
                                         C.byref(batch), C.byref(outs), C.byref(scratch), stream)
         nat.check(rc, "t2n_render_forward")
         model._last_counters = sc["counters"]
+        if need_bwd:
+            model._post_listed_count(sc["counters"])
         model._last_scratch = sc if os.environ.get("T2N_KEEP_SCRATCH") else None
         if need_bwd:
             ctx.model = model
@@ -299,6 +306,12 @@ class _RenderFn(torch.autograd.Function):
         gstruct = model._native_grads(grads)
         if model._is_mlp:
             sc["w1_grad_packed"] = torch.empty_like(sc["w1_packed"])
+        if sc["act_rows"]:
+            npack = int(lib.t2n_bwd_pack_floats(C.byref(field)))
+            row_bytes = int(lib.t2n_bwd_image_row_bytes(C.byref(field)))
+            if npack and row_bytes:
+                sc["bwd_pack"] = torch.empty((npack,), device=dev, dtype=torch.float32)
+                sc["bwd_img"] = torch.empty((sc["act_rows"] * row_bytes,), device=dev, dtype=torch.uint8)
         mask = model.alphaMask.native() if model.alphaMask is not None else None
         batch = nat.T2NBatch(_ptr(rays), _ptr(jitter) if jitter.numel() else None, R, S, int(is_train), int(white_bg))
         outs = nat.T2NOutputs(_ptr(rgb_map), None, _ptr(z_vals), _ptr(weight))
@@ -654,6 +667,39 @@ class TensorBase(torch.nn.Module):
             buf = torch.empty((n,), device=device, dtype=torch.float32)
             self._mma_pack = buf
         return buf
+
+    # ---- capacity of the tensor-core backward's per-sample state ---------------------------------------
+    # The number of listed samples (weight > rayMarch_weight_thres) of a batch is only known on the device.
+    # Instead of synchronising, every training forward posts an asynchronous copy of the counter to pinned
+    # memory; later forwards fold completed copies into a running maximum that sizes the next allocation.
+    def _act_capacity(self, R, S):
+        import os
+        seen = getattr(self, "_listed_seen", 0)
+        rows = max(int(1.25 * seen) + 1024, 48 * R) if seen else 96 * R
+        rows = min(rows, R * S, int(os.environ.get("T2N_ACT_ROWS_MAX", 6 << 20)))
+        return max(128, (rows + 127) // 128 * 128)
+
+    def _post_listed_count(self, counters):
+        pend = getattr(self, "_listed_pending", None)
+        if pend is None:
+            pend = self._listed_pending = []
+        if len(pend) >= 4:
+            return
+        pool = getattr(self, "_listed_pool", None)
+        if pool is None:
+            pool = self._listed_pool = [(torch.empty((8,), dtype=torch.int32).pin_memory(), torch.cuda.Event())
+                                        for _ in range(4)]
+        host, ev = pool.pop(0)
+        host.copy_(counters, non_blocking=True)
+        ev.record()
+        pend.append((host, ev))
+
+    def _poll_listed_count(self):
+        pend = getattr(self, "_listed_pending", None)
+        while pend and pend[0][1].query():
+            host, ev = pend.pop(0)
+            self._listed_seen = max(int(0.98 * getattr(self, "_listed_seen", 0)), int(host[0]))
+            self._listed_pool.append((host, ev))
 
     def _w1_packed_buffer(self, device):
         if not self._is_mlp:
