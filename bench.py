@@ -346,7 +346,7 @@ def main():
         bk = dict(nat.profile_read())
         lib.t2n_profile_enable(0)
         fwd_bwd["kernel_ms"] = {**fk, **bk}
-        launches_train = 7 * TRAIN_BATCHES_PER_STEP * args.steps
+        launches_train = 15 * TRAIN_BATCHES_PER_STEP * args.steps    # march, pack, app, finalize | pack_bwd, bwd-data, 4 wgrad, (pack_w1, ffma fallback, unpack: early exit), ray_backward
         model.enable_flat_grads(False)
 
     # ---------------- CPU baseline (rank 0, N=1 only)

@@ -146,7 +146,9 @@ typedef struct T2NOutputs {
  *   slots      R*S int32                                     compacted list of samples with
  *                                                            weight > weight_thres, value r*S+k
  *   app_rgb    3*R*S float                                   decoder output per listed sample
- *   counters   8 int32  (zeroed by the library)              [0]=#listed, [1]=#valid sigma samples
+ *   counters   8 int32  (zeroed by the library)              [0]=#listed, [1]=#valid sigma samples; after a
+ *                                                            backward [2]=#128-sample tiles the tensor-core backward
+ *                                                            took, [3]=#CTAs of the FFMA backward that did work
  *   w1_packed  feature_c*mlp_in_pad float                    column-permuted copy of w1
  *   ray_flags  R int32                                       bit c set iff rgb_map[.,c] was inside
  *                                                            [0,1] before the clamp (clamp backward)

@@ -41,7 +41,7 @@ def test_wgrad_gemm_vs_float64(ngx, ngy, n, cuda_device):
     rows = 32 * ngx
     scale = float(ref.abs().max())
     err = float((out[:rows].cpu().double() - ref).abs().max()) / scale
-    assert err < 2e-6, err
+    assert err < 2e-6 * max(1.0, (n / 4096) ** 0.5), err
     ref1 = X.double().sum(0)
     err1 = float((ones[:rows].cpu().double() - ref1).abs().max()) / float(ref1.abs().max())
     assert err1 < 2e-6, err1
@@ -72,6 +72,13 @@ def test_overflow_fallback_matches_tensor_core_path(name, cuda_device, monkeypat
         out = render_with_jitter(model, c.rays.to(cuda_device), c.jitter, True, c.white_eff, c.n_samples)
         listed = model.app_sample_count()[0]
         orc.training_loss(*out, c.rgb_gt.to(cuda_device), c.depth_gt.to(cuda_device)).backward()
+        cnt = model._last_counters.cpu()
+        from text2nerf_b200 import _native as nat
+        in_envelope = nat.load().t2n_bwd_pack_floats(C.byref(model._native_field())) > 0
+        if tag == "mma" and in_envelope:
+            assert int(cnt[2]) == (listed + 127) // 128 and int(cnt[3]) == 0, cnt
+        else:
+            assert int(cnt[2]) == 0 and int(cnt[3]) > 0, cnt
         res[tag] = (_grads(model), listed)
     assert res["mma"][1] == res["ffma"][1] > 128, "the case must overflow a 128-row capacity"
     for k, g in res["mma"][0].items():
@@ -81,3 +88,30 @@ def test_overflow_fallback_matches_tensor_core_path(name, cuda_device, monkeypat
             continue
         assert scaled_err(g, g2) <= 2e-4, (k, scaled_err(g, g2))
         assert cosine(g, g2) > 1 - 1e-6, k
+
+
+def test_tensor_core_backward_covers_view_dependent_heads(cuda_device):
+    """MLP_Fea / MLP heads (view-direction columns, two PE groups) inside the tensor-core envelope (featureC 128,
+    16-multiple component counts) against oracle autograd."""
+    for shading, fea_pe, view_pe in (("MLP_Fea", 2, 2), ("MLP", 6, 4), ("MLP_Fea_noview", 6, 2)):
+        spec = orc.FieldSpec(aabb=[[-8, -8, -8], [8, 8, 8]], grid=[40, 44, 48], near_far=[0.5, 8.0], step_ratio=1.0,
+                             shading=shading, fea_pe=fea_pe, view_pe=view_pe)
+        params = orc.init_params(spec, seed=11, density_gain=10.8, app_gain=3.0)
+        g = torch.Generator().manual_seed(5)
+        R = 300
+        d = torch.cat([0.5 * (torch.rand(R, 2, generator=g) * 2 - 1), torch.ones(R, 1)], -1)
+        rays = torch.cat([0.05 * torch.randn(R, 3, generator=g), d / d.norm(dim=-1, keepdim=True)], -1)
+        jitter = torch.rand(R, 1, generator=g)
+        S = orc.derive_step(spec)[1] // 2
+        rgb_gt, depth_gt = torch.rand(R, 3, generator=g), 0.5 + 7 * torch.rand(R, generator=g)
+        p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        orc.training_loss(*orc.render(spec, p_ref, rays, S, True, True, jitter), rgb_gt, depth_gt).backward()
+        model = build_model(spec, params, cuda_device)
+        out = render_with_jitter(model, rays.to(cuda_device), jitter, True, True, S)
+        orc.training_loss(*out, rgb_gt.to(cuda_device), depth_gt.to(cuda_device)).backward()
+        cnt = model._last_counters.cpu()
+        assert int(cnt[2]) == (int(cnt[0]) + 127) // 128 > 0 and int(cnt[3]) == 0, (shading, cnt)
+        for k, p in model.named_parameters():
+            gr = p_ref[k].grad
+            assert scaled_err(p.grad, gr) <= 2e-4, (shading, k, scaled_err(p.grad, gr))
+            assert cosine(p.grad, gr) > 1 - 1e-6, (shading, k)

@@ -43,8 +43,38 @@ struct RayBwdArgs {
     const float* g_weight;      // nullable
 };
 
+__device__ __forceinline__ void red_add_smem(float* p, float v) {
+    asm volatile("red.shared.add.f32 [%0], %1;" :: "r"(smem_u32(p)), "f"(v) : "memory");
+}
+
+// Sum float4 values over runs of lane groups (grp = lane >> 2, 8 groups of 4 channel lanes) that carry the same key.
+// The 8 groups hold consecutive samples of one ray; a shuffle-down doubling scan restricted to runs (no run start
+// between the two groups) leaves each run's total in its first group.
+__device__ __forceinline__ void seg_reduce_groups(unsigned heads, int grp, float4& va, float4& vb) {
+    // heads: ballot of "this group starts a run"; group g may absorb group g+off only if no run starts in (g, g+off]
+    const unsigned after = grp < 7 ? heads >> (4 * (grp + 1)) : 0u;
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+        float4 a2, b2;
+        a2.x = __shfl_down_sync(T2N_FULL, va.x, 4 * off); a2.y = __shfl_down_sync(T2N_FULL, va.y, 4 * off);
+        a2.z = __shfl_down_sync(T2N_FULL, va.z, 4 * off); a2.w = __shfl_down_sync(T2N_FULL, va.w, 4 * off);
+        b2.x = __shfl_down_sync(T2N_FULL, vb.x, 4 * off); b2.y = __shfl_down_sync(T2N_FULL, vb.y, 4 * off);
+        b2.z = __shfl_down_sync(T2N_FULL, vb.z, 4 * off); b2.w = __shfl_down_sync(T2N_FULL, vb.w, 4 * off);
+        if (grp + off < 8 && (after & ((1u << (4 * off)) - 1u)) == 0u) {
+            va.x += a2.x; va.y += a2.y; va.z += a2.z; va.w += a2.w;
+            vb.x += b2.x; vb.y += b2.y; vb.z += b2.z; vb.w += b2.w;
+        }
+    }
+}
+
+// Scatter of one step: every lane of the warp calls this (shuffles inside); `active` lanes own a sample with a
+// non-zero density-feature gradient df.  Plane texels get red.global.add.v4; the line gradients of the 8 samples
+// are first summed over runs of samples that hit the same line texels (neighbouring samples along a ray move a
+// fraction of a texel, the slow axes not at all), then only the run heads touch the accumulators -- the
+// shared-memory float atomic is a CAS loop (ATOMS.CAST.SPIN) that serialises on every same-address conflict.
 template <int NQ>
-__device__ __forceinline__ void sigma_scatter(const RayBwdArgs& a, float* const* gl, const Axis ax[3], int c4, float df) {
+__device__ __forceinline__ void sigma_scatter(const RayBwdArgs& a, float* const* gl, const Axis ax[3], int c4, int grp,
+                                              bool active, float df) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const int a0 = (i == 2) ? 1 : 0;
@@ -62,10 +92,16 @@ __device__ __forceinline__ void sigma_scatter(const RayBwdArgs& a, float* const*
         float* GP = a.gsp[i];
         const size_t o00 = ((size_t)Y.c0 * W + X.c0) * C, o01 = ((size_t)Y.c0 * W + X.c1) * C;
         const size_t o10 = ((size_t)Y.c1 * W + X.c0) * C, o11 = ((size_t)Y.c1 * W + X.c1) * C;
+        const int key = active ? (Z.c0 | (Z.c1 << 16)) : (-1 - grp);
+        const int key_prev = __shfl_up_sync(T2N_FULL, key, 4);
+        const bool starts = grp == 0 || key_prev != key;        // inactive groups carry unique keys: runs never span them
+        const unsigned heads = __ballot_sync(T2N_FULL, starts);
+        const bool head = active && starts;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int ch = (q * 4 + c4) * 4;
-            if (ch < C) {
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            if (active && ch < C) {
                 float4 t00 = ldg4(P + o00 + ch), t01 = ldg4(P + o01 + ch);
                 float4 t10 = ldg4(P + o10 + ch), t11 = ldg4(P + o11 + ch);
                 float4 l0 = ldg4(L + Z.c0 * C + ch), l1 = ldg4(L + Z.c1 * C + ch);
@@ -77,14 +113,25 @@ __device__ __forceinline__ void sigma_scatter(const RayBwdArgs& a, float* const*
                 if (ne != 0.f) red_add_v4(GP + o01 + ch, f4_scale(ne, dpl));
                 if (sw != 0.f) red_add_v4(GP + o10 + ch, f4_scale(sw, dpl));
                 if (se != 0.f) red_add_v4(GP + o11 + ch, f4_scale(se, dpl));
+                va = f4_scale(Z.w0, dln);
+                vb = f4_scale(Z.w1, dln);
+            }
+            seg_reduce_groups(heads, grp, va, vb);
+            if (head && ch < C) {
                 float* g0 = gl[i] + Z.c0 * C + ch;
                 float* g1 = gl[i] + Z.c1 * C + ch;
                 if (a.lines_in_smem) {
-                    if (Z.w0 != 0.f) { atomicAdd(g0, Z.w0 * dln.x); atomicAdd(g0 + 1, Z.w0 * dln.y); atomicAdd(g0 + 2, Z.w0 * dln.z); atomicAdd(g0 + 3, Z.w0 * dln.w); }
-                    if (Z.w1 != 0.f) { atomicAdd(g1, Z.w1 * dln.x); atomicAdd(g1 + 1, Z.w1 * dln.y); atomicAdd(g1 + 2, Z.w1 * dln.z); atomicAdd(g1 + 3, Z.w1 * dln.w); }
+                    if (va.x != 0.f) red_add_smem(g0, va.x);
+                    if (va.y != 0.f) red_add_smem(g0 + 1, va.y);
+                    if (va.z != 0.f) red_add_smem(g0 + 2, va.z);
+                    if (va.w != 0.f) red_add_smem(g0 + 3, va.w);
+                    if (vb.x != 0.f) red_add_smem(g1, vb.x);
+                    if (vb.y != 0.f) red_add_smem(g1 + 1, vb.y);
+                    if (vb.z != 0.f) red_add_smem(g1 + 2, vb.z);
+                    if (vb.w != 0.f) red_add_smem(g1 + 3, vb.w);
                 } else {
-                    if (Z.w0 != 0.f) red_add_v4(g0, f4_scale(Z.w0, dln));
-                    if (Z.w1 != 0.f) red_add_v4(g1, f4_scale(Z.w1, dln));
+                    red_add_v4(g0, va);
+                    red_add_v4(g1, vb);
                 }
             }
         }
@@ -190,7 +237,7 @@ __global__ void __launch_bounds__(256) ray_backward_kernel(const __grid_constant
                         ax[q] = make_axis(i0, fr, f.G[q]);
                     }
                     const float dfs = __shfl_sync(T2N_FULL, df, src);
-                    if ((sub >> grp) & 1u) sigma_scatter<NQ>(a, gl, ax, c4, dfs);
+                    sigma_scatter<NQ>(a, gl, ax, c4, grp, ((sub >> grp) & 1u) != 0, dfs);
                 }
             }
         }
@@ -313,6 +360,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = a.counters[0];
     if (b.skip_if_le >= 0 && (long long)total <= b.skip_if_le) return;
+    if (tid == 0 && blockIdx.x * kTM < total) atomicAdd(const_cast<int32_t*>(a.counters) + 3, 1);   // path marker
     const int C = a.C;
     const int NA = a.n_app_total;
     const bool mlp = a.shading <= T2N_SHADE_MLP;

@@ -4,7 +4,7 @@
 namespace t2n {
 int launch_pack_bwd(const BwdPackArgs& a, cudaStream_t st) {
     const BwdPack P = bwd_pack_layout(a.n_app_total, a.Kp);
-    const int groups = 4 * 128 * 8 + P.w1_chunks * 4 * 32 * 8 + P.b_chunks * 32 * 8;
+    const int groups = 4 * 128 * 8 + P.w1_super * 4 * 128 * 8 + P.b_pieces * 128 * 8;
     pack_bwd_weights_kernel<<<(groups + 255) / 256, 256, 0, st>>>(a);
     return (int)cudaGetLastError();
 }

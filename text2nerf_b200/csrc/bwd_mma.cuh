@@ -14,7 +14,7 @@
 // One persistent CTA per SM, tiles of 128 listed samples; 16 producer/epilogue warps + 1 issuer warp as in the
 // forward (appearance_mma.cuh).  The A operand of every GEMM lives in TMEM (TS mode: dz2, then dz1, then dfeat
 // reuse columns 256..511), B operands are pre-swizzled weight images streamed by TMA through a 4-deep ring.
-// TMEM: [0,128) dh1, later dprod [0,160) | [128,256) ring of four dA chunks | [256,512) A operand (4 x hi|lo).
+// TMEM: [0,128) dh1, then dA ring slot 1, later dprod [0,160) | [128,256) dA ring slot 0 | [256,512) A operand (4 x hi|lo).
 // Per tile the phases run back to back (no cross-tile pipelining yet):
 //   P1  dz3 = w G y(1-y);  dz2 = (dz3 . W3) [h2 > 0]              -> TMEM A, dz2 / dz3 images, db3
 //   M1  dh1                                                         (issuer)
@@ -33,38 +33,41 @@ namespace t2n {
 // One thread per (tile row, 16-byte column group) of every weight image.
 static __global__ void pack_bwd_weights_kernel(const __grid_constant__ BwdPackArgs a) {
     const BwdPack P = bwd_pack_layout(a.n_app_total, a.Kp);
-    const int n_w2 = 4 * 128 * 8, n_w1 = P.w1_chunks * 4 * 32 * 8, n_b = P.b_chunks * 32 * 8;
+    const int n_w2 = 4 * 128 * 8, n_w1 = P.w1_super * 4 * 128 * 8, n_b = P.b_pieces * 128 * 8;
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_w2 + n_w1 + n_b) return;
     float v[4];
     float* dst_hi;
-    int rows, r;
+    int rows;
     const int j = g & 7;
+    const int r = (g >> 3) & 127;
     if (g < n_w2) {
         const int kc = g / (128 * 8);
-        r = (g >> 3) % 128; rows = 128;
+        rows = 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] = a.w2[(size_t)(32 * kc + 4 * j + q) * 128 + r];
         dst_hi = a.out + P.w2_off + (size_t)kc * 2 * 128 * 32;
     } else if ((g -= n_w2) < n_w1) {
-        const int t = g / (32 * 8);                 // tile index = c * 4 + kc
-        const int c = t >> 2, kc = t & 3;
-        r = (g >> 3) % 32; rows = 32;
-        const int src = a.perm[32 * c + r];
+        const int t = g / (128 * 8);                // sc * 4 + kc
+        const int sc = t >> 2, kc = t & 3;
+        rows = bwd_group_rows(P.w1_chunks, sc);
+        if (r >= rows) return;
+        const int src = a.perm[128 * sc + r];
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] = src >= 0 ? a.w1[(size_t)(32 * kc + 4 * j + q) * a.K + src] : 0.f;
-        dst_hi = a.out + P.w1_off + (size_t)t * 2 * 32 * 32;
+        dst_hi = a.out + P.w1_off + (size_t)sc * 4 * 2 * 128 * 32 + (size_t)kc * 2 * rows * 32;
     } else {
         g -= n_w1;
-        const int jb = g / (32 * 8);
-        r = (g >> 3) % 32; rows = 32;
-        const int comp = 32 * jb + r;
+        const int pc = g / (128 * 8);
+        rows = bwd_group_rows(P.b_chunks, pc);
+        if (r >= rows) return;
+        const int comp = 128 * pc + r;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int b = a.own[4 * j + q];
             v[q] = (b < a.app_dim && comp < a.n_app_total) ? a.basis[(size_t)b * a.n_app_total + comp] : 0.f;
         }
-        dst_hi = a.out + P.b_off + (size_t)jb * 2 * 32 * 32;
+        dst_hi = a.out + P.b_off + (size_t)pc * 2 * 128 * 32;
     }
     float* dst_lo = dst_hi + rows * 32;
     const uint32_t off = sw128_off(r, j) >> 2;
@@ -93,16 +96,18 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
     if (n_tiles == 0) return;
     const BwdPack P = bwd_pack_layout(a.n_app_total, args.Kp);
     const int ngc = P.w1_chunks, ngp = P.b_chunks;
-    const int NCH = 4 + ngc + ngp;          // weight chunks per tile
+    const int nsc = P.w1_super, npc = P.b_pieces;
+    const int NCH = 4 + 4 * nsc + npc;      // weight chunks (TMA loads) per tile
 
+    if (tid == 0) atomicAdd(const_cast<int32_t*>(a.counters) + 2, n_tiles);     // path marker: tiles taken by this kernel
     float* w3s = reinterpret_cast<float*>(sm + L.w3);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint64_t* bar_bfull = bars;             // [4] weight chunk landed
     uint64_t* bar_done = bars + 4;          // [4] MMAs that read the weight stage completed
     uint64_t* bar_a = bars + 8;             // A operand written by the 16 producer warps (3 uses per tile)
     uint64_t* bar_acc = bars + 9;           // [2] dh1 complete / dprod complete
-    uint64_t* bar_rfull = bars + 12;        // [4] dA chunk in ring slot complete
-    uint64_t* bar_rfree = bars + 16;        // [4] ring slot read by all producer warps
+    uint64_t* bar_rfull = bars + 12;        // [2] dA super-chunk in ring slot complete
+    uint64_t* bar_rfree = bars + 16;        // [2] ring slot read by all producer warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
 
     for (int i = tid; i < 3 * 128; i += kMmaThreads) w3s[i] = __ldg(a.w3 + i);
@@ -124,14 +129,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
 
     if (warp == kProdWarps) {
         // =========================== ISSUER ===========================
-        const uint32_t idesc128 = umma_idesc_tf32(128), idesc32 = umma_idesc_tf32(32);
+        const uint32_t idesc128 = umma_idesc_tf32(128);
         const uint32_t tm = __shfl_sync(T2N_FULL, tmem, 0);
         const uint32_t smb = __shfl_sync(T2N_FULL, sm_addr, 0);
         const uint32_t bars_addr = smb + L.bars;
         const int terms = args.terms;
         const uint32_t n_chunks = (uint32_t)n_tiles * NCH;
         uint32_t loaded = 0, it = 0, a_uses = 0;
-        uint32_t ring_fill[4] = {0, 0, 0, 0};
+        uint32_t ring_fill[2] = {0, 0};
         auto prefetch = [&](uint32_t upto) {
             while (loaded < upto && loaded < n_chunks) {
                 const uint32_t bs = loaded % kBwdNB;
@@ -139,8 +144,15 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                 const int pos = (int)(loaded % NCH);
                 const float* src; uint32_t bytes;
                 if (pos < 4) { src = args.pack + P.w2_off + (size_t)pos * 2 * 128 * 32; bytes = 2 * kTileBytes; }
-                else if (pos < 4 + ngc) { src = args.pack + P.w1_off + (size_t)(pos - 4) * 4 * 2 * 32 * 32; bytes = 2 * kTileBytes; }
-                else { src = args.pack + P.b_off + (size_t)(pos - 4 - ngc) * 2 * 32 * 32; bytes = 2 * 32 * 128; }
+                else if (pos < 4 + 4 * nsc) {
+                    const int sc = (pos - 4) >> 2, kc = (pos - 4) & 3, nr = bwd_group_rows(ngc, sc);
+                    src = args.pack + P.w1_off + (size_t)sc * 4 * 2 * 128 * 32 + (size_t)kc * 2 * nr * 32;
+                    bytes = 2 * nr * 128;
+                } else {
+                    const int pc = pos - 4 - 4 * nsc;
+                    src = args.pack + P.b_off + (size_t)pc * 2 * 128 * 32;
+                    bytes = 2 * bwd_group_rows(ngp, pc) * 128;
+                }
                 tma_load_elect(smb + L.b[bs], src, bytes, bars_addr + 8 * bs);
                 ++loaded;
             }
@@ -170,45 +182,49 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                 prefetch(it + kBwdNB - 1);
             }
             umma_commit_elect(bars_addr + 8 * 9);                  // bar_acc[0]: dh1 complete
-            // ---- M2: dA chunk c = dz1 . W1b[:, c]   (A: TMEM, B: W1T chunk c = 4 K-chunks, N = 32) -> ring slot c & 3
+            // ---- M2: dA super-chunk sc = dz1 . W1b[:, 128sc ..]  (A: TMEM, B: one stage per K-chunk, N = 32 * chunks) -> ring slot sc & 1
             mbar_wait(bar_a, a_uses & 1); ++a_uses;
             tc_fence_after();
-            for (int c = 0; c < ngc; ++c, ++it) {
-                const uint32_t bs = wait_b();
-                const int rs = c & 3;
+            for (int sc = 0; sc < nsc; ++sc) {
+                const int rs = sc & 1;
+                const int nr = bwd_group_rows(ngc, sc);
+                const uint32_t idesc = umma_idesc_tf32(nr);
                 if (ring_fill[rs] > 0) mbar_wait(bar_rfree + rs, (ring_fill[rs] - 1) & 1);
                 ++ring_fill[rs];
                 tc_fence_after();
-                const uint32_t d = tm + kBwdColRing + 32 * rs;
-#pragma unroll
-                for (int kc = 0; kc < 4; ++kc) {
-                    const uint32_t bh = desc_lo(smb + L.b[bs] + kc * 8192), bl = bh + (4096 >> 4);
+                const uint32_t d = tm + (rs ? kBwdColDH1 : kBwdColRing);
+                for (int kc = 0; kc < 4; ++kc, ++it) {
+                    const uint32_t bs = wait_b();
+                    tc_fence_after();
+                    const uint32_t bh = desc_lo(smb + L.b[bs]), bl = bh + ((nr * 128) >> 4);
                     const uint32_t ta = tm + kBwdColA + 64 * kc;
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc32, (kc | kk) != 0);
-                        if (terms & 2) umma_ts_elect(d, ta + 32 + 8 * kk, bh + 2 * kk, kDescHi, idesc32, 1);
-                        if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc32, 1);
+                        umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc, (kc | kk) != 0);
+                        if (terms & 2) umma_ts_elect(d, ta + 32 + 8 * kk, bh + 2 * kk, kDescHi, idesc, 1);
+                        if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc, 1);
                     }
+                    umma_commit_elect(bars_addr + 8 * (4 + bs));
+                    prefetch(it + kBwdNB - 1);
                 }
-                umma_commit_elect(bars_addr + 8 * (4 + bs));
                 umma_commit_elect(bars_addr + 8 * (12 + rs));      // bar_rfull[rs]
-                prefetch(it + kBwdNB - 1);
             }
-            // ---- M3: dprod[:, 32j..] = dfeat . basis   (A: TMEM chunk 0, B: BT chunk j, N = 32, K = 32)
+            // ---- M3: dprod[:, 128p ..] = dfeat . basis   (A: TMEM chunk 0, B: BT piece p, N = 32 * chunks, K = 32)
             mbar_wait(bar_a, a_uses & 1); ++a_uses;
             tc_fence_after();
-            for (int j = 0; j < ngp; ++j, ++it) {
+            for (int pc = 0; pc < npc; ++pc, ++it) {
                 const uint32_t bs = wait_b();
                 tc_fence_after();
-                const uint32_t bh = desc_lo(smb + L.b[bs]), bl = bh + (4096 >> 4);
+                const int nr = bwd_group_rows(ngp, pc);
+                const uint32_t idesc = umma_idesc_tf32(nr);
+                const uint32_t bh = desc_lo(smb + L.b[bs]), bl = bh + ((nr * 128) >> 4);
                 const uint32_t ta = tm + kBwdColA;
-                const uint32_t d = tm + kBwdColDH1 + 32 * j;
+                const uint32_t d = tm + kBwdColDH1 + 128 * pc;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc32, kk != 0);
-                    if (terms & 2) umma_ts_elect(d, ta + 32 + 8 * kk, bh + 2 * kk, kDescHi, idesc32, 1);
-                    if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc32, 1);
+                    umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc, kk != 0);
+                    if (terms & 2) umma_ts_elect(d, ta + 32 + 8 * kk, bh + 2 * kk, kDescHi, idesc, 1);
+                    if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc, 1);
                 }
                 umma_commit_elect(bars_addr + 8 * (4 + bs));
                 prefetch(it + kBwdNB - 1);
@@ -219,7 +235,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
         // =========================== PRODUCERS / EPILOGUES ===========================
         const int m = tid & 127, q = tid >> 7;                  // tile row (= TMEM lane) and column quarter / entry group
         const uint32_t tmem_lane = (uint32_t)(32 * (warp & 3)) << 16;
-        uint32_t ring_take[4] = {0, 0, 0, 0};
+        uint32_t ring_take[2] = {0, 0};
         auto publish_a = [&]() {
             tmem_st_wait();
             tc_fence_before();
@@ -332,21 +348,29 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                 bv[i] = x;
                 g[i] = 0.f;
             }
+            // ring slot of decoder-column chunk c: super-chunk c / 4 lives in slot (c / 4) & 1, columns 32 (c & 3) ..
             auto ring_wait = [&](int c) {
-                const int s = c & 3;
-                mbar_wait(bar_rfull + s, ring_take[s] & 1);
-                ++ring_take[s];
-                tc_fence_after();
+                if ((c & 3) == 0) {
+                    const int s = (c >> 2) & 1;
+                    mbar_wait(bar_rfull + s, ring_take[s] & 1);
+                    ++ring_take[s];
+                    tc_fence_after();
+                }
+            };
+            auto ring_addr = [&](int c) {
+                return tmem + tmem_lane + (((c >> 2) & 1) ? kBwdColDH1 : kBwdColRing) + 32 * (c & 3) + 8 * q;
             };
             auto ring_release = [&](int c) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_rfree + (c & 3));
+                if ((c & 3) == 3 || c == ngc - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_rfree + ((c >> 2) & 1));
+                }
             };
             {   // chunk 0: identity columns
                 uint32_t dv[8];
                 ring_wait(0);
-                tmem_ld8(tmem + tmem_lane + kBwdColRing + 8 * q, dv);
+                tmem_ld8(ring_addr(0), dv);
                 ring_release(0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) g[i] += __uint_as_float(dv[i]);
@@ -374,7 +398,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                     const int c = 1 + f * args.pe_chunks + h;
                     uint32_t dv[8];
                     ring_wait(c);
-                    tmem_ld8(tmem + tmem_lane + kBwdColRing + 32 * (c & 3) + 8 * q, dv);
+                    tmem_ld8(ring_addr(c), dv);
                     ring_release(c);
                     float cols[8];
 #pragma unroll

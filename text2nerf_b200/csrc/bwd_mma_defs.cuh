@@ -47,22 +47,32 @@ inline bool build_mma_bwd_recipe(const MmaRecipe& R, int app_dim, MmaBwdRecipe& 
 }
 
 // Weight images of the backward-data GEMMs (floats; K-major SWIZZLE_128B tiles, TF32 hi then lo):
-//   W2T   4 chunks kc   : [128 rows k][32 cols n = 32kc..]            value W2[n][k]        (dh1 = dz2 . W2)
-//   W1T   Kp/32 chunks c: 4 x { hi [32 rows j][32 cols n = 32kc..], lo }  value W1b[n][32c+j]  (dA_c = dz1 . W1b_c)
-//   BT    ceil(NA/32) j : { hi [32 rows comp][32 cols s], lo }         value basis[own[s]][32j+comp]  (dprod = dfeat . basis)
+//   W2T   4 chunks kc                 : [128 rows k][32 cols n = 32kc..]        value W2[n][k]     (dh1 = dz2 . W2)
+//   W1T   super-chunk sc (<= 4 decoder-column chunks = nr <= 128 rows), K-chunk kc:
+//                                       [nr rows j][32 cols n = 32kc..]          value W1b[n][128sc+j]   (dA = dz1 . W1b)
+//   BT    piece p (<= 128 components)  : [nr rows comp][32 cols s]               value basis[own[s]][128p+comp]
+// Small-N MMAs cost ~48 cycles whatever N is (tools/mma_rate.cu: N=32 48 cyc, N=128 64 cyc), so the data GEMMs
+// run at N = 128 wherever the shapes allow.
 struct BwdPack {
-    int w1_chunks, b_chunks;
+    int w1_chunks, b_chunks;        // 32-column chunks of the decoder input / of the product vector
+    int w1_super, b_pieces;         // groups of <= 4 chunks
     size_t w2_off, w1_off, b_off, total;        // floats
 };
 __host__ __device__ inline BwdPack bwd_pack_layout(int n_app_total, int Kp) {
     BwdPack P;
     P.w1_chunks = Kp / 32;
     P.b_chunks = (n_app_total + 31) / 32;
+    P.w1_super = (P.w1_chunks + 3) / 4;
+    P.b_pieces = (P.b_chunks + 3) / 4;
     P.w2_off = 0;
     P.w1_off = (size_t)4 * 2 * 128 * 32;
-    P.b_off = P.w1_off + (size_t)P.w1_chunks * 4 * 2 * 32 * 32;
-    P.total = P.b_off + (size_t)P.b_chunks * 2 * 32 * 32;
+    P.b_off = P.w1_off + (size_t)P.w1_super * 4 * 2 * 128 * 32;
+    P.total = P.b_off + (size_t)P.b_pieces * 2 * 128 * 32;
     return P;
+}
+__host__ __device__ inline int bwd_group_rows(int chunks, int g) {      // rows of group g of a chunk list
+    const int left = chunks - 4 * g;
+    return 32 * (left < 4 ? left : 4);
 }
 
 // Per-row bytes of the images the backward-data kernel writes for the weight-gradient GEMMs
@@ -72,8 +82,8 @@ __host__ __device__ inline size_t bwd_img_row_bytes(int n_app_total, int Kp) {
 }
 
 constexpr int kBwdNB = 4;               // weight-chunk ring depth (32 KB stages)
-constexpr int kBwdColDH1 = 0;           // dh1 accumulator [0,128); later dprod [0, 32*b_chunks)
-constexpr int kBwdColRing = 128;        // dA ring: 4 x 32 columns
+constexpr int kBwdColDH1 = 0;           // dh1 accumulator [0,128); then dA ring slot 1; later dprod [0, 32*b_chunks)
+constexpr int kBwdColRing = 128;        // dA ring slot 0 [128,256): one super-chunk of <= 4 decoder-column chunks
 constexpr int kBwdColA = 256;           // A operand in TMEM: 4 K-chunks x (hi 32 | lo 32)
 
 struct BwdSmem {

@@ -675,7 +675,7 @@ class TensorBase(torch.nn.Module):
     def _act_capacity(self, R, S):
         import os
         seen = getattr(self, "_listed_seen", 0)
-        rows = max(int(1.25 * seen) + 1024, 48 * R) if seen else 96 * R
+        rows = max(int(1.25 * seen) + 1024, 48 * R, 8192) if seen else max(96 * R, 8192)
         rows = min(rows, R * S, int(os.environ.get("T2N_ACT_ROWS_MAX", 6 << 20)))
         return max(128, (rows + 127) // 128 * 128)
 

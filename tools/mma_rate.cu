@@ -112,7 +112,7 @@ int main() {
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const char* names[] = {"tf32 SS", "tf32 TS", "bf16 SS (K=16)", "tf32 SS 2 accumulators", "tf32 SS warp-uniform elect", "tf32 SS elect + shfl-uniform", "tf32 TS uniform elect", "tf32 TS uniform 3-term pattern (per MMA)"};
     for (int mode = 4; mode < 8; ++mode)
-        for (int N : {128, 256}) {
+        for (int N : {16, 32, 64, 128, 256}) {
             if (mode == 3 && N != 128) continue;
             for (int grid : {148}) {
                 const int reps = 2000;

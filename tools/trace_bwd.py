@@ -35,8 +35,17 @@ buf = (C.c_longlong * 32)()
 nat.load().t2n_debug_trace_read(buf)
 v = list(buf)
 nt = max(v[12], 1)
-names = ["gather+basis", "decoder fwd recompute", "L3 fwd/bwd,dW3,dz2", "dW2+red", "dh1->dz1", "L1bwd: load+columns", "dW1+red",
-         "dA+PE bwd", "basis bwd", "scatter", "-", "loop overhead"]
-print("tiles of CTA0:", v[12], " total cycles/tile:", sum(v[:12]) / nt)
-for n, c in zip(names, v[:12]):
-    print(f"  {n:24s} {c / nt:10.0f} cyc/tile  {100 * c / max(sum(v[:12]), 1):5.1f}%")
+if os.environ.get("T2N_BWD_FFMA"):
+    names = ["gather+basis", "decoder fwd recompute", "L3 fwd/bwd,dW3,dz2", "dW2+red", "dh1->dz1", "L1bwd: load+columns", "dW1+red",
+             "dA+PE bwd", "basis bwd", "scatter", "-", "loop overhead"]
+    nt = max(v[12], 1)
+    print("FFMA kernel, tiles of CTA0:", v[12], " total cycles/tile:", sum(v[:12]) / nt)
+    tot = sum(v[:12])
+else:
+    names = ["P1 dz3,dz2 -> TMEM + images", "wait dh1 MMA", "P2 dz1 -> TMEM + image", "P3 dA ring: PE backward + column images",
+             "P4 dfeat", "P5 gather + products image + dprod + scatter"]
+    nt = max(v[8], 1)
+    print("tensor-core backward-data kernel, tiles (128 samples) of CTA0:", v[8], " total cycles/tile:", sum(v[:6]) / nt)
+    tot = sum(v[:6])
+for n, c in zip(names, v[:len(names)]):
+    print(f"  {n:44s} {c / nt:10.0f} cyc/tile  {100 * c / max(tot, 1):5.1f}%")
