@@ -400,7 +400,6 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
             d.cap_rows = cap_rows;
             d.dz2_img = img;  img += (size_t)cap_rows * 1024;
             d.dz1_img = img;  img += (size_t)cap_rows * 1024;
-            d.cols_img = img; img += (size_t)cap_rows * 256 * ngc;
             d.dfeat_img = img; img += (size_t)cap_rows * 256;
             d.prod_img = img; img += (size_t)cap_rows * 256 * ngp;
             d.dz3_img = img;
@@ -433,7 +432,10 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
             rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
             if (rc) return rc;
             // dW1[n][perm[k]] = sum dz1[m][n] cols[m][k], db1
-            base(d.dz1_img, 4, d.cols_img, ngc, grads->w1, grads->b1);
+            base(d.dz1_img, 4, d.dz1_img /* unused: columns are regenerated */, ngc, grads->w1, grads->b1);
+            w.gen_cols = 1; w.feat = scratch->act_feat; w.rays = batch->rays; w.slots = scratch->slots; w.S = batch->S;
+            w.app_dim = field->app_dim; w.n_freq = R.n_freq; w.pe_chunks = R.pe_chunks;
+            memcpy(w.own, RB.own, 32); memcpy(w.pe_nf, R.pe_nf, 32);
             for (int n = 0; n < 128; ++n) { w.row_off[n] = n * field->mlp_in; w.row_off_ones[n] = n; }
             for (int k = 0; k < 32 * ngc; ++k) w.col_off[k] = RB.perm[k];
             rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);

@@ -6,8 +6,8 @@
 //      dA_c  = dz1 . W1b[:, c]     [128 x 32 x 128]  per 32-column chunk c of the decoder input
 //      dprod = dfeat . basis       [128 x NA x 32]
 // the positional-encoding backward and the scatter-add into the appearance planes / lines
-// (grid_sampler_2d_backward).  Weight gradients are NOT formed here: the kernel writes dz2, dz1, the decoder
-// input columns, dfeat, the plane*line products and dz3 as MN-major operand images and wgrad_mma.cuh contracts
+// (grid_sampler_2d_backward).  Weight gradients are NOT formed here: the kernel writes dz2, dz1, dfeat, the
+// plane*line products and dz3 as MN-major operand images and wgrad_mma.cuh contracts
 // them over the samples with accumulators that persist in TMEM (a fused kernel would need 128 + Kp > 512 TMEM
 // columns for dW2 | dW1 on top of the data accumulators).
 //
@@ -20,7 +20,7 @@
 //   M1  dh1                                                         (issuer)
 //   P2  dz1 = dh1 [h1 > 0]                                         -> TMEM A, dz1 image
 //   M2/P3  dA chunk c -> ring; producers: identity / (sin, cos) chain backward into 8 thread-owned base
-//          entries, decoder-column image of the chunk
+//          entries
 //   P4  dfeat                                                      -> TMEM A, dfeat image
 //   M3  dprod
 //   P5  gather plane/line texels (8 channels per thread), products image, dprod from TMEM, red.v4 scatter
@@ -262,7 +262,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
             const bool live = e < total;
             uint8_t* dz2_t = args.dz2_img + (size_t)tile * img_tile_bytes(4);
             uint8_t* dz1_t = args.dz1_img + (size_t)tile * img_tile_bytes(4);
-            uint8_t* cols_t = args.cols_img + (size_t)tile * img_tile_bytes(ngc);
             uint8_t* dfeat_t = args.dfeat_img + (size_t)tile * img_tile_bytes(1);
             uint8_t* prod_t = args.prod_img + (size_t)tile * img_tile_bytes(ngp);
             uint8_t* dz3_t = args.dz3_img + (size_t)tile * img_tile_bytes(1);
@@ -374,7 +373,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                 ring_release(0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) g[i] += __uint_as_float(dv[i]);
-                img_store8(cols_t, ngc, m, 0, q, bv);
             }
             float sn[8], cs[8];
 #pragma unroll
@@ -400,16 +398,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                     ring_wait(c);
                     tmem_ld8(ring_addr(c), dv);
                     ring_release(c);
-                    float cols[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float s_ = h ? sn[4 + i] : sn[i], c_ = h ? cs[4 + i] : cs[i];
                         const int nfi = h ? nf[4 + i] : nf[i];
-                        cols[2 * i] = s_; cols[2 * i + 1] = c_;
                         const float d = scale * (c_ * __uint_as_float(dv[2 * i]) - s_ * __uint_as_float(dv[2 * i + 1]));
                         if (f < nfi) { if (h) g[4 + i] += d; else g[i] += d; }
                     }
-                    img_store8(cols_t, ngc, m, c, q, cols);
                 }
             }
             mark(3);

@@ -76,9 +76,10 @@ __host__ __device__ inline int bwd_group_rows(int chunks, int g) {      // rows 
 }
 
 // Per-row bytes of the images the backward-data kernel writes for the weight-gradient GEMMs
-// (dz2, dz1: 4 groups; decoder columns: Kp/32 groups; dfeat, dz3: 1 group; products: ceil(NA/32) groups).
+// (dz2, dz1: 4 groups; dfeat, dz3: 1 group; products: ceil(NA/32) groups).  The decoder input columns (Kp/32
+// groups, the largest operand) are NOT materialised: the dW1 GEMM regenerates them from the saved features.
 __host__ __device__ inline size_t bwd_img_row_bytes(int n_app_total, int Kp) {
-    return (size_t)256 * (4 + 4 + Kp / 32 + 1 + 1 + (n_app_total + 31) / 32);
+    return (size_t)256 * (4 + 4 + 1 + 1 + (n_app_total + 31) / 32);
 }
 
 constexpr int kBwdNB = 4;               // weight-chunk ring depth (32 KB stages)
@@ -121,7 +122,7 @@ struct BwdMmaArgs {
     const float* feat;          // [rows][32] base vector (feature part)
     long long cap_rows;
     // images written here
-    uint8_t* dz2_img; uint8_t* dz1_img; uint8_t* cols_img; uint8_t* dfeat_img; uint8_t* prod_img; uint8_t* dz3_img;
+    uint8_t* dz2_img; uint8_t* dz1_img; uint8_t* dfeat_img; uint8_t* prod_img; uint8_t* dz3_img;
     // gradients accumulated directly
     float* gap[3]; float* gal[3];
     float* g_b3;
@@ -137,7 +138,7 @@ struct BwdPackArgs {
 };
 
 // ---- weight-gradient GEMM kernel (wgrad_mma.cuh)
-constexpr int kWgradThreads = 128;
+constexpr int kWgradThreads = 192;         // warp 0 loader, warp 1 issuer, warps 2..5 column producers; warps 0..3 flush
 constexpr int kMaxYGroups = 13;
 struct WgradArgs {
     const uint8_t* x_img;       // ngx groups per row (4, or 1: the single group is aliased onto all four M groups
@@ -153,6 +154,15 @@ struct WgradArgs {
     int32_t row_off[128];
     int32_t row_off_ones[128];
     int32_t col_off[kMaxYGroups * 32];
+    // gen_cols != 0: Y is not an image -- warps 2..5 regenerate the decoder input columns of every 16-sample block
+    // (backward column order: identity slots, then (sin, cos) chunks per frequency) straight into the stage
+    int gen_cols;
+    const float* feat;          // [rows][32]
+    const float* rays;          // view-direction entries
+    const int32_t* slots;
+    int S, app_dim, n_freq, pe_chunks;
+    unsigned char own[32];
+    unsigned char pe_nf[32];
 };
 
 }  // namespace t2n

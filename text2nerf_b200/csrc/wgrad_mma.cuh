@@ -27,6 +27,7 @@ namespace t2n {
 __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
     return ((smem_addr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
 }
+constexpr int kWgradProdWarps = 4;
 constexpr uint32_t kDescHiMn = (uint32_t)((512u >> 4) | (1u << 14) | (1u << 29));
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int n) {   // D=f32, A=B=tf32, both MN-major, M=128
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
     __syncthreads();
     if (tid < kImgBlockRows) *reinterpret_cast<float*>(ones_tile + tid * 128 + img_chunk_pos(tid, 0)) = 1.0f;
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, 1); }
+        for (int i = 0; i < NS; ++i) { mbar_init(bar_full + i, a.gen_cols ? 1 + kWgradProdWarps : 1); mbar_init(bar_empty + i, 1); }
         mbar_init(bar_final, 1);
         mbar_fence_init();
     }
@@ -87,15 +88,16 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
                 asm volatile(
                     "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
                     "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
-                    :: "r"(bar), "r"(xb + yb) : "memory");
+                    :: "r"(bar), "r"(a.gen_cols ? xb : xb + yb) : "memory");
                 asm volatile(
                     "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
                     "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
                     :: "r"(dst), "l"(xt + (size_t)blk * xb), "r"(xb), "r"(bar) : "memory");
-                asm volatile(
-                    "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-                    "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
-                    :: "r"(dst + xb), "l"(yt + (size_t)blk * yb), "r"(yb), "r"(bar) : "memory");
+                if (!a.gen_cols)
+                    asm volatile(
+                        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+                        :: "r"(dst + xb), "l"(yt + (size_t)blk * yb), "r"(yb), "r"(bar) : "memory");
             }
         }
     } else if (warp == 1) {
@@ -137,12 +139,90 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
         }
         umma_commit_elect(smb + (uint32_t)((uint8_t*)bar_final - sm));
     }
+    else if (warp >= 2 && a.gen_cols) {
+        // =========================== COLUMN PRODUCERS (dW1): Y block = decoder input columns of 16 samples ===========================
+        // thread = (sample row r of the block, entry group eg): 4 base-vector slots 4eg..4eg+3 = identity columns 4eg+i of
+        // chunk 0 and, for frequency f, the (sin, cos) pairs at columns 8ph + 2i of chunk 1 + f*pe_chunks + h (ph = eg/2, h = eg&1)
+        const int pt = tid - 64;
+        const int r = pt & 15, eg = pt >> 4;
+        const int ph = eg >> 1, h = eg & 1;
+        const uint32_t y_lo_off = (uint32_t)ngy * kImgGroupBytes;
+        int own[4], nf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            own[i] = a.own[4 * eg + i];
+            nf[i] = a.pe_nf[(h ? 16 : 0) + 4 * ph + i];
+        }
+        const bool has_chunk = h < a.pe_chunks;
+        const int row_sw = r & 3;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+            for (int blk = 0; blk < 8; ++blk, ++it) {
+                const uint32_t s = it % NS;
+                const int e = t * 128 + blk * 16 + r;
+                float bv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float x = 0.f;
+                    if (e < total) {
+                        if (own[i] < a.app_dim) x = __ldg(a.feat + (size_t)e * 32 + own[i]);
+                        else if (own[i] < a.app_dim + 3) x = __ldg(a.rays + (size_t)(__ldg(a.slots + e) / a.S) * 6 + 3 + (own[i] - a.app_dim));
+                    }
+                    bv[i] = x;
+                }
+                float sn[4], cs[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    sn[i] = 0.f; cs[i] = 1.f;
+                    if (nf[i] > 0) sincosf(bv[i], &sn[i], &cs[i]);
+                }
+                if (it >= (uint32_t)NS) mbar_wait(bar_empty + s, ((it / NS) - 1) & 1);
+                uint8_t* yrow = sm + (size_t)s * stage_bytes + xb + r * 128;       // row r of group 0, hi half
+                {   // chunk 0, columns 4eg .. 4eg+3: half of 32-byte chunk eg/2
+                    uint32_t hh[4], ll[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { hh[i] = tf32_hi(bv[i]); ll[i] = __float_as_uint(bv[i] - __uint_as_float(hh[i])); }
+                    uint8_t* p0 = yrow + (((eg >> 1) ^ row_sw) << 5) + ((eg & 1) << 4);
+                    *reinterpret_cast<uint4*>(p0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                    *reinterpret_cast<uint4*>(p0 + y_lo_off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                }
+                for (int f = 0; f < a.n_freq; ++f) {
+                    if (f > 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float s2 = 2.f * sn[i];
+                            const float ns = s2 * cs[i];
+                            cs[i] = fmaf(-s2, sn[i], 1.f);
+                            sn[i] = ns;
+                        }
+                    }
+                    if (has_chunk) {
+                        const int c = 1 + f * a.pe_chunks + h;
+                        uint8_t* p0 = yrow + (size_t)c * kImgGroupBytes + ((ph ^ row_sw) << 5);      // columns 8ph .. 8ph+7
+                        uint32_t hh[8], ll[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            hh[2 * i] = tf32_hi(sn[i]); ll[2 * i] = __float_as_uint(sn[i] - __uint_as_float(hh[2 * i]));
+                            hh[2 * i + 1] = tf32_hi(cs[i]); ll[2 * i + 1] = __float_as_uint(cs[i] - __uint_as_float(hh[2 * i + 1]));
+                        }
+                        reinterpret_cast<uint4*>(p0)[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                        reinterpret_cast<uint4*>(p0)[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+                        reinterpret_cast<uint4*>(p0 + y_lo_off)[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                        reinterpret_cast<uint4*>(p0 + y_lo_off)[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + s);
+            }
+        }
+    }
     __syncwarp();
 
     // =========================== FLUSH: D[lane][col] -> red.global.add ===========================
     mbar_wait(bar_final, 0);
     tc_fence_after();
-    {
+    if (warp < 4) {
         const int row = 32 * warp + lane;
         const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
         const int ro = a.row_off[row];
