@@ -138,7 +138,7 @@ struct BwdPackArgs {
 };
 
 // ---- weight-gradient GEMM kernel (wgrad_mma.cuh)
-constexpr int kWgradThreads = 192;         // warp 0 loader, warp 1 issuer, warps 2..5 column producers; warps 0..3 flush
+constexpr int kWgradThreads = 320;         // warp 0 loader, warp 1 issuer, warps 2..9 column producers; warps 0..3 flush
 constexpr int kMaxYGroups = 13;
 struct WgradArgs {
     const uint8_t* x_img;       // ngx groups per row (4, or 1: the single group is aliased onto all four M groups

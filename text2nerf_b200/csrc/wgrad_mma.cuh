@@ -27,7 +27,7 @@ namespace t2n {
 __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
     return ((smem_addr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
 }
-constexpr int kWgradProdWarps = 4;
+constexpr int kWgradProdWarps = 8;
 constexpr uint32_t kDescHiMn = (uint32_t)((512u >> 4) | (1u << 14) | (1u << 29));
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int n) {   // D=f32, A=B=tf32, both MN-major, M=128
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -141,17 +141,17 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
     }
     else if (warp >= 2 && a.gen_cols) {
         // =========================== COLUMN PRODUCERS (dW1): Y block = decoder input columns of 16 samples ===========================
-        // thread = (sample row r of the block, entry group eg): 4 base-vector slots 4eg..4eg+3 = identity columns 4eg+i of
-        // chunk 0 and, for frequency f, the (sin, cos) pairs at columns 8ph + 2i of chunk 1 + f*pe_chunks + h (ph = eg/2, h = eg&1)
+        // thread = (sample row r of the block, entry group eg = 0..15): 2 base-vector slots 2eg, 2eg+1 = identity columns of
+        // chunk 0 and, for frequency f, two (sin, cos) pairs at columns 8ph + 2(i0 + i) of chunk 1 + f*pe_chunks + h
         const int pt = tid - 64;
         const int r = pt & 15, eg = pt >> 4;
-        const int ph = eg >> 1, h = eg & 1;
+        const int ph = eg >> 2, h = (eg >> 1) & 1, i0 = 2 * (eg & 1);
         const uint32_t y_lo_off = (uint32_t)ngy * kImgGroupBytes;
-        int own[4], nf[4];
+        int own[2], nf[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            own[i] = a.own[4 * eg + i];
-            nf[i] = a.pe_nf[(h ? 16 : 0) + 4 * ph + i];
+        for (int i = 0; i < 2; ++i) {
+            own[i] = a.own[2 * eg + i];
+            nf[i] = a.pe_nf[(h ? 16 : 0) + 4 * ph + i0 + i];
         }
         const bool has_chunk = h < a.pe_chunks;
         const int row_sw = r & 3;
@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
             for (int blk = 0; blk < 8; ++blk, ++it) {
                 const uint32_t s = it % NS;
                 const int e = t * 128 + blk * 16 + r;
-                float bv[4];
+                float bv[2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     float x = 0.f;
                     if (e < total) {
                         if (own[i] < a.app_dim) x = __ldg(a.feat + (size_t)e * 32 + own[i]);
@@ -170,26 +170,26 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
                     }
                     bv[i] = x;
                 }
-                float sn[4], cs[4];
+                float sn[2], cs[2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     sn[i] = 0.f; cs[i] = 1.f;
                     if (nf[i] > 0) sincosf(bv[i], &sn[i], &cs[i]);
                 }
                 if (it >= (uint32_t)NS) mbar_wait(bar_empty + s, ((it / NS) - 1) & 1);
                 uint8_t* yrow = sm + (size_t)s * stage_bytes + xb + r * 128;       // row r of group 0, hi half
-                {   // chunk 0, columns 4eg .. 4eg+3: half of 32-byte chunk eg/2
-                    uint32_t hh[4], ll[4];
+                {   // chunk 0, columns 2eg, 2eg+1: 8 bytes of 32-byte chunk ph
+                    uint32_t hh[2], ll[2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { hh[i] = tf32_hi(bv[i]); ll[i] = __float_as_uint(bv[i] - __uint_as_float(hh[i])); }
-                    uint8_t* p0 = yrow + (((eg >> 1) ^ row_sw) << 5) + ((eg & 1) << 4);
-                    *reinterpret_cast<uint4*>(p0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                    *reinterpret_cast<uint4*>(p0 + y_lo_off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                    for (int i = 0; i < 2; ++i) { hh[i] = tf32_hi(bv[i]); ll[i] = __float_as_uint(bv[i] - __uint_as_float(hh[i])); }
+                    uint8_t* p0 = yrow + ((ph ^ row_sw) << 5) + ((eg & 3) << 3);
+                    *reinterpret_cast<uint2*>(p0) = make_uint2(hh[0], hh[1]);
+                    *reinterpret_cast<uint2*>(p0 + y_lo_off) = make_uint2(ll[0], ll[1]);
                 }
                 for (int f = 0; f < a.n_freq; ++f) {
                     if (f > 0) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < 2; ++i) {
                             const float s2 = 2.f * sn[i];
                             const float ns = s2 * cs[i];
                             cs[i] = fmaf(-s2, sn[i], 1.f);
@@ -198,17 +198,15 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
                     }
                     if (has_chunk) {
                         const int c = 1 + f * a.pe_chunks + h;
-                        uint8_t* p0 = yrow + (size_t)c * kImgGroupBytes + ((ph ^ row_sw) << 5);      // columns 8ph .. 8ph+7
-                        uint32_t hh[8], ll[8];
+                        uint8_t* p0 = yrow + (size_t)c * kImgGroupBytes + ((ph ^ row_sw) << 5) + ((eg & 1) << 4);   // columns 8ph + 2 i0 ..
+                        uint32_t hh[4], ll[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < 2; ++i) {
                             hh[2 * i] = tf32_hi(sn[i]); ll[2 * i] = __float_as_uint(sn[i] - __uint_as_float(hh[2 * i]));
                             hh[2 * i + 1] = tf32_hi(cs[i]); ll[2 * i + 1] = __float_as_uint(cs[i] - __uint_as_float(hh[2 * i + 1]));
                         }
-                        reinterpret_cast<uint4*>(p0)[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                        reinterpret_cast<uint4*>(p0)[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-                        reinterpret_cast<uint4*>(p0 + y_lo_off)[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-                        reinterpret_cast<uint4*>(p0 + y_lo_off)[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+                        *reinterpret_cast<uint4*>(p0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                        *reinterpret_cast<uint4*>(p0 + y_lo_off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
                     }
                 }
                 fence_async_smem();
