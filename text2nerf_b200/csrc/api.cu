@@ -280,6 +280,8 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
             memcpy(ma2.ident_src, R.ident_src, 32); memcpy(ma2.pe_src, R.pe_src, 32); memcpy(ma2.pe_nf, R.pe_nf, 32);
             const char* tenv = getenv("T2N_MMA_TERMS");          // accuracy study hook; default 3xTF32
             ma2.terms = tenv ? atoi(tenv) : 7;
+            const char* benv = getenv("T2N_MMA_BACKOFF_NS");
+            ma2.backoff_ns = benv ? (unsigned)atoi(benv) : 64u;
             if (getenv("T2N_MMA_TRACE")) {                       // debug cycle counters of CTA 0
                 if (!g_trace) cudaMalloc(&g_trace, 32 * sizeof(long long));
                 cudaMemsetAsync(g_trace, 0, 32 * sizeof(long long), st);

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
     uint64_t* bar_bfull = bars;         // [kNB] B chunk landed (TMA complete_tx)
     uint64_t* bar_done = bars + 4;      // [4] MMAs of chunk it (slot it % 4) have completed (tcgen05.commit): frees A stage
                                         //     it & 1 for the producers and B stage it % kNB for the weight prefetcher
-    uint64_t* bar_afull = bars + 10;    // [2] A chunk written by all 16 producer warps
+    uint64_t* bar_afull = bars + 8;     // [4] A chunk written by all 16 producer warps (ring of 4: producers run up to 3 chunks ahead)
     uint64_t* bar_acc = bars + 12;      // [3] accumulator D0 / D1 / D2 of a tile complete (tcgen05.commit)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
 
@@ -146,8 +146,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
     if (tid < 3) b3s[tid] = __ldg(a.b3 + tid);
     if (tid == 0) {
         for (int i = 0; i < 10; ++i) mbar_init(bars + i, 1);
-        mbar_init(bar_afull + 0, kProdWarps);
-        mbar_init(bar_afull + 1, kProdWarps);
+        for (int i = 0; i < 4; ++i) mbar_init(bar_afull + i, kProdWarps);
         for (int i = 0; i < 3; ++i) mbar_init(bar_acc + i, 1);
         mbar_fence_init();
     }
@@ -164,7 +163,37 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
     int n_tiles = 0;
     for (int tile = blockIdx.x; tile * kMmaM < total; tile += gridDim.x) ++n_tiles;
 
-    if (warp == kProdWarps) {
+    // the chunk sequence all roles walk: iteration j = [S2 of tile j-2][S1 of tile j-1][S0 of tile j]
+    auto group_valid = [&](int j, int g) {
+        const int t = j - (2 - g);      // g=0 -> tile j-2, g=1 -> tile j-1, g=2 -> tile j
+        return t >= 0 && t < n_tiles;
+    };
+    auto group_len = [&](int g) { return g == 0 ? nk2 : (g == 1 ? nk1 : nk0); };
+
+    if (warp == kProdWarps + 1) {
+        // =========================== WEIGHT LOADER ===========================
+        // A dedicated warp streams the B chunks: a 32 KB bulk copy occupies the SM's TMA engine for ~700 cycles and the
+        // instruction that issues the next one waits for it, which must not happen in the thread that feeds the tensor pipe.
+        if (n_tiles > 0) {
+            const uint32_t smb = __shfl_sync(T2N_FULL, sm_addr, 0);
+            const uint32_t bars_addr = smb + L.bars;
+            uint32_t loaded = 0;
+            for (int j = 0; j < n_tiles + 2; ++j)
+                for (int g = 0; g < 3; ++g) {
+                    if (!group_valid(j, g)) continue;
+                    const int len = group_len(g);
+                    for (int c = 0; c < len; ++c, ++loaded) {
+                        const uint32_t bs = loaded % kNB;
+                        if (loaded >= kNB) mbar_wait(bar_done + bs, ((loaded / kNB) - 1) & 1);
+                        const float* src; uint32_t bytes;
+                        if (g == 2) { src = args.pack + P.basis_off + (size_t)c * 2 * 32 * 32; bytes = 2 * 32 * 128; }
+                        else if (g == 1) { src = args.pack + P.w1_off + (size_t)c * 2 * 128 * 32; bytes = 2 * kTileBytes; }
+                        else { src = args.pack + P.w2_off + (size_t)c * 2 * 128 * 32; bytes = 2 * kTileBytes; }
+                        tma_load_elect(smb + L.b[bs], src, bytes, bars_addr + 8 * bs);
+                    }
+                }
+        }
+    } else if (warp == kProdWarps) {
         // =========================== ISSUER ===========================
         if (n_tiles > 0) {
             const uint32_t idesc128 = umma_idesc_tf32(128), idesc32 = umma_idesc_tf32(32);
@@ -172,38 +201,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             const uint32_t smb = __shfl_sync(T2N_FULL, sm_addr, 0);
             const uint32_t bars_addr = smb + L.bars;
             const int terms = args.terms;
-            // the chunk sequence both sides walk: iteration j = [S2 of tile j-2][S1 of tile j-1][S0 of tile j]
-            uint32_t it = 0, loaded = 0;
-            int lj = 0, lg = 0, lc = 0;         // cursor of the B prefetcher: iteration, group (0=S2,1=S1,2=S0), chunk
-            auto group_valid = [&](int j, int g) {
-                const int t = j - (2 - g);      // g=0 -> tile j-2, g=1 -> tile j-1, g=2 -> tile j
-                return t >= 0 && t < n_tiles;
-            };
-            auto group_len = [&](int g) { return g == 0 ? nk2 : (g == 1 ? nk1 : nk0); };
-            auto advance = [&](int& j, int& g, int& c) {      // move the cursor to the next existing chunk
-                ++c;
-                while (j < n_tiles + 2 && (!group_valid(j, g) || c >= group_len(g))) {
-                    c = 0;
-                    if (++g == 3) { g = 0; ++j; }
-                }
-            };
-            while (lj < n_tiles + 2 && !group_valid(lj, lg)) { if (++lg == 3) { lg = 0; ++lj; } }
-            auto prefetch = [&](uint32_t upto) {        // issue B loads for chunks < upto whose stage is free
-                while (loaded < upto && lj < n_tiles + 2) {
-                    const uint32_t bs = loaded % kNB;
-                    if (loaded >= kNB) mbar_wait(bar_done + bs, ((loaded / kNB) - 1) & 1);
-                    const float* src; uint32_t bytes;
-                    if (lg == 2) { src = args.pack + P.basis_off + (size_t)lc * 2 * 32 * 32; bytes = 2 * 32 * 128; }
-                    else if (lg == 1) { src = args.pack + P.w1_off + (size_t)lc * 2 * 128 * 32; bytes = 2 * kTileBytes; }
-                    else { src = args.pack + P.w2_off + (size_t)lc * 2 * 128 * 32; bytes = 2 * kTileBytes; }
-                    tma_load_elect(smb + L.b[bs], src, bytes, bars_addr + 8 * bs);
-                    ++loaded;
-                    advance(lj, lg, lc);
-                }
-            };
+            uint32_t it = 0;
             const bool tr = args.trace != nullptr && blockIdx.x == 0 && lane == 0;
             long long w_af = 0, w_bf = 0, t_is = 0, t_pf = 0, t0i = clock64();
-            prefetch(kNB - 1);
             for (int j = 0; j < n_tiles + 2; ++j)
                 for (int g = 0; g < 3; ++g) {
                     if (!group_valid(j, g)) continue;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                         long long c0 = clock64();
                         mbar_wait(bar_bfull + bs, (it / kNB) & 1);
                         long long c1 = clock64();
-                        mbar_wait(bar_afull + (it & 1), (it >> 1) & 1);
+                        mbar_wait(bar_afull + (it & 3), (it >> 2) & 1);
                         long long c2 = clock64();
                         tc_fence_after();
                         const uint32_t bh = desc_lo(smb + L.b[bs]);
@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                                 if (terms & 4) umma_ss_elect(d, ah + 2 * kk, bl + 2 * kk, kDescHi, idesc, 1);
                             }
                         } else {                            // decoder layers: A from tensor memory (hi | lo), N = 128
-                            const uint32_t ta = tm + kColA + 64 * (it & 1), bl = bh + (kTileBytes >> 4);
+                            const uint32_t ta = tm + kColA + 64 * (it % kTmemAStages), bl = bh + (kTileBytes >> 4);
+                            if (terms == 7) umma_ts_chunk_3x(d, ta, bh, bl, kDescHi, idesc, c != 0);
+                            else
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
                                 umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc, (c | kk) != 0);
@@ -239,8 +241,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                         umma_commit_elect(bars_addr + 8 * (4 + bs));               // bar_done[it % 4]
                         if (c == len - 1) umma_commit_elect(bars_addr + 8 * (12 + (2 - g)));   // bar_acc: g=0 -> D2, 1 -> D1, 2 -> D0
                         long long c3 = clock64();
-                        prefetch(it + kNB - 1);         // chunk it+2 reuses the B stage of chunk it-2 (long done): no stall
-                        long long c4 = clock64();
+                        long long c4 = c3;
                         w_bf += c1 - c0; w_af += c2 - c1; t_is += c3 - c2; t_pf += c4 - c3;
                     }
                 }
@@ -255,26 +256,29 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
         long long tS[4] = {0, 0, 0, 0}, wAcc[3] = {0, 0, 0}, wSt[3] = {0, 0, 0}, t0p = clock64();
         int cur_stage = 0;
         uint32_t it = 0;        // chunks produced so far by this CTA (ring position)
-        auto stage_acquire = [&](uint32_t i) {
+        auto stage_acquire = [&](uint32_t i, bool smem_stage = false) {
             const long long c0 = clock64();
-            if (i >= 2) mbar_wait(bar_done + ((i - 2) & 3), ((i - 2) >> 2) & 1);    // chunk i-2 used this A stage
+            // shared-memory A stages (basis chunks) form a ring of 2, TMEM A stages (decoder layers) a ring of kTmemAStages:
+            // the stage is free once the chunk that last used it (at most `back` chunks ago) has completed
+            const uint32_t back = smem_stage ? 2u : (uint32_t)kTmemAStages;
+            if (i >= back) mbar_wait_backoff(bar_done + ((i - back) & 3), ((i - back) >> 2) & 1, args.backoff_ns);
             wSt[cur_stage] += clock64() - c0;
         };
         auto stage_publish = [&](uint32_t i) {          // generic-proxy writes -> async proxy, then one arrival per warp
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_afull + (i & 1));
+            if (lane == 0) mbar_arrive(bar_afull + (i & 3));
         };
         auto stage_publish_tmem = [&](uint32_t i) {     // tcgen05.st writes complete, then one arrival per warp
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_afull + (i & 1));
+            if (lane == 0) mbar_arrive(bar_afull + (i & 3));
         };
         auto acc_wait = [&](int which, int local_tile) {     // accumulator `which` (0=D0,1=D1,2=D2) of the CTA's n-th tile
             const long long c0 = clock64();
-            mbar_wait(bar_acc + which, local_tile & 1);
+            mbar_wait_backoff(bar_acc + which, local_tile & 1, args.backoff_ns);
             wAcc[which] += clock64() - c0;
             tc_fence_after();
         };
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                     if (args.h1_img != nullptr && e_row < args.act_rows)        // operand image for the backward (all 128 rows)
                         img_store8(args.h1_img + (size_t)(e_row >> 7) * img_tile_bytes(4), 4, erow, c, eq, h);
                     stage_acquire(it);
-                    st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it & 1), eq * 8, h);
+                    st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), eq * 8, h);
                     stage_publish_tmem(it);
                 }
             }
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
 #pragma unroll
                     for (int q = 0; q < 8; ++q) c0[q] = brow[id_src[q]];
                     stage_acquire(it);
-                    st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it & 1), 8 * ph, c0);
+                    st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), 8 * ph, c0);
                     stage_publish_tmem(it);
                     ++it;
                 }
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                             cols[2 * q + 1] = h ? cs[4 + q] : cs[q];
                         }
                         stage_acquire(it);
-                        st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it & 1), 8 * ph, cols);
+                        st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), 8 * ph, cols);
                         stage_publish_tmem(it);
                     }
                 }
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                             prod[q] = f4_mul(pv, lv);
                         }
                     }
-                    stage_acquire(it);                          // loads above overlap the wait
+                    stage_acquire(it, true);                    // loads above overlap the wait
                     uint8_t* A_hi = sm + L.a[it & 1];
                     uint8_t* A_lo = A_hi + kTileBytes;
 #pragma unroll

@@ -12,7 +12,8 @@ constexpr int kStageA = 2 * kTileBytes; // hi + lo
 constexpr int kStageB = 2 * kTileBytes;
 constexpr int kTmemCols = 512;
 constexpr int kColD1 = 0, kColD2 = 128, kColD0 = 256;   // three accumulators live at once (tiles j-1, j-2, j)
-constexpr int kColA = 320;              // A operand of the decoder layers lives in TMEM: 2 stages x (hi 32 | lo 32) columns
+constexpr int kColA = 320;              // A operand of the decoder layers lives in TMEM: 3 stages x (hi 32 | lo 32) columns = [320, 512)
+constexpr int kTmemAStages = 3;
 constexpr int kBaseStride = 39;         // odd, >= app_dim + 7 for app_dim <= 32 (feature | viewdir | xyz | 0)
 constexpr int kMaxFreq = 10;
 
@@ -143,6 +144,7 @@ struct AppMmaArgs {
     uint8_t* h2_img;        // relu(D2 + b2), same format
     float* feat;            // [rows][32] appearance feature (basis output), zero padded
     long long act_rows;     // capacity of the three arrays in rows (multiple of 128)
+    unsigned backoff_ns;    // nanosleep between polls of the producers' long mbarrier waits
     long long* trace;       // debug: 32 cycle counters written by CTA 0 (NULL = off), see t2n_debug_trace_read
 };
 

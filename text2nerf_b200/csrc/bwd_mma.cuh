@@ -127,7 +127,29 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == kProdWarps) {
+    if (warp == kProdWarps + 1) {
+        // =========================== WEIGHT LOADER (dedicated warp: see appearance_mma.cuh) ===========================
+        const uint32_t smb = __shfl_sync(T2N_FULL, sm_addr, 0);
+        const uint32_t bars_addr = smb + L.bars;
+        const uint32_t n_chunks = (uint32_t)n_tiles * NCH;
+        for (uint32_t loaded = 0; loaded < n_chunks; ++loaded) {
+            const uint32_t bs = loaded % kBwdNB;
+            if (loaded >= kBwdNB) mbar_wait(bar_done + bs, ((loaded / kBwdNB) - 1) & 1);
+            const int pos = (int)(loaded % NCH);
+            const float* src; uint32_t bytes;
+            if (pos < 4) { src = args.pack + P.w2_off + (size_t)pos * 2 * 128 * 32; bytes = 2 * kTileBytes; }
+            else if (pos < 4 + 4 * nsc) {
+                const int sc = (pos - 4) >> 2, kc = (pos - 4) & 3, nr = bwd_group_rows(ngc, sc);
+                src = args.pack + P.w1_off + (size_t)sc * 4 * 2 * 128 * 32 + (size_t)kc * 2 * nr * 32;
+                bytes = 2 * nr * 128;
+            } else {
+                const int pc = pos - 4 - 4 * nsc;
+                src = args.pack + P.b_off + (size_t)pc * 2 * 128 * 32;
+                bytes = 2 * bwd_group_rows(ngp, pc) * 128;
+            }
+            tma_load_elect(smb + L.b[bs], src, bytes, bars_addr + 8 * bs);
+        }
+    } else if (warp == kProdWarps) {
         // =========================== ISSUER ===========================
         const uint32_t idesc128 = umma_idesc_tf32(128);
         const uint32_t tm = __shfl_sync(T2N_FULL, tmem, 0);
@@ -135,34 +157,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
         const uint32_t bars_addr = smb + L.bars;
         const int terms = args.terms;
         const uint32_t n_chunks = (uint32_t)n_tiles * NCH;
-        uint32_t loaded = 0, it = 0, a_uses = 0;
+        uint32_t it = 0, a_uses = 0;
         uint32_t ring_fill[2] = {0, 0};
-        auto prefetch = [&](uint32_t upto) {
-            while (loaded < upto && loaded < n_chunks) {
-                const uint32_t bs = loaded % kBwdNB;
-                if (loaded >= kBwdNB) mbar_wait(bar_done + bs, ((loaded / kBwdNB) - 1) & 1);
-                const int pos = (int)(loaded % NCH);
-                const float* src; uint32_t bytes;
-                if (pos < 4) { src = args.pack + P.w2_off + (size_t)pos * 2 * 128 * 32; bytes = 2 * kTileBytes; }
-                else if (pos < 4 + 4 * nsc) {
-                    const int sc = (pos - 4) >> 2, kc = (pos - 4) & 3, nr = bwd_group_rows(ngc, sc);
-                    src = args.pack + P.w1_off + (size_t)sc * 4 * 2 * 128 * 32 + (size_t)kc * 2 * nr * 32;
-                    bytes = 2 * nr * 128;
-                } else {
-                    const int pc = pos - 4 - 4 * nsc;
-                    src = args.pack + P.b_off + (size_t)pc * 2 * 128 * 32;
-                    bytes = 2 * bwd_group_rows(ngp, pc) * 128;
-                }
-                tma_load_elect(smb + L.b[bs], src, bytes, bars_addr + 8 * bs);
-                ++loaded;
-            }
-        };
         auto wait_b = [&]() {
             const uint32_t bs = it % kBwdNB;
             mbar_wait(bar_bfull + bs, (it / kBwdNB) & 1);
             return bs;
         };
-        prefetch(kBwdNB - 1);
         for (int t = 0; t < n_tiles; ++t) {
             // ---- M1: dh1 = dz2 . W2   (A: TMEM chunks kc, B: W2T chunk kc, N = 128)
             mbar_wait(bar_a, a_uses & 1); ++a_uses;
@@ -172,6 +173,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                 tc_fence_after();
                 const uint32_t bh = desc_lo(smb + L.b[bs]), bl = bh + (kTileBytes >> 4);
                 const uint32_t ta = tm + kBwdColA + 64 * kc;
+                if (terms == 7) umma_ts_chunk_3x(tm + kBwdColDH1, ta, bh, bl, kDescHi, idesc128, kc != 0);
+                else
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     umma_ts_elect(tm + kBwdColDH1, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc128, (kc | kk) != 0);
@@ -179,7 +182,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                     if (terms & 4) umma_ts_elect(tm + kBwdColDH1, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc128, 1);
                 }
                 umma_commit_elect(bars_addr + 8 * (4 + bs));
-                prefetch(it + kBwdNB - 1);
             }
             umma_commit_elect(bars_addr + 8 * 9);                  // bar_acc[0]: dh1 complete
             // ---- M2: dA super-chunk sc = dz1 . W1b[:, 128sc ..]  (A: TMEM, B: one stage per K-chunk, N = 32 * chunks) -> ring slot sc & 1
@@ -198,6 +200,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                     tc_fence_after();
                     const uint32_t bh = desc_lo(smb + L.b[bs]), bl = bh + ((nr * 128) >> 4);
                     const uint32_t ta = tm + kBwdColA + 64 * kc;
+                    if (terms == 7) umma_ts_chunk_3x(d, ta, bh, bl, kDescHi, idesc, kc != 0);
+                    else
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc, (kc | kk) != 0);
@@ -205,7 +209,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                         if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc, 1);
                     }
                     umma_commit_elect(bars_addr + 8 * (4 + bs));
-                    prefetch(it + kBwdNB - 1);
                 }
                 umma_commit_elect(bars_addr + 8 * (12 + rs));      // bar_rfull[rs]
             }
@@ -220,6 +223,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                 const uint32_t bh = desc_lo(smb + L.b[bs]), bl = bh + ((nr * 128) >> 4);
                 const uint32_t ta = tm + kBwdColA;
                 const uint32_t d = tm + kBwdColDH1 + 128 * pc;
+                if (terms == 7) umma_ts_chunk_3x(d, ta, bh, bl, kDescHi, idesc, 0);
+                else
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc, kk != 0);
@@ -227,7 +232,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
                     if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc, 1);
                 }
                 umma_commit_elect(bars_addr + 8 * (4 + bs));
-                prefetch(it + kBwdNB - 1);
             }
             umma_commit_elect(bars_addr + 8 * 10);                 // bar_acc[1]: dprod complete
         }

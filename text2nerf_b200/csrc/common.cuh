@@ -202,6 +202,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "T2N_DONE_%=:\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same, for waits that are expected to take long (producer warps waiting for MMA completion): back off between
+// polls so that 16 spinning warps do not compete with the tensor core's operand reads for shared memory.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0)
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -94,6 +94,43 @@ __device__ __forceinline__ void umma_ts_elect(uint32_t tmem_d, uint32_t tmem_a, 
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
         :: "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc) : "memory");
 }
+// One K chunk (4 k-steps of 8) of a 3xTF32 GEMM in ONE asm block: a single elect.sync, descriptors formed with immediate
+// offsets, twelve tcgen05.mma back to back.  Per-MMA asm blocks cost ~16 SASS instructions and ~100 cycles of dependent
+// issue latency each in the (register-pressured, scheduler-shared) issuer warp, more than the 64 cycles the MMA takes.
+// a_step: TMEM column step of the A operand per k-step (8); lo half of A at +32 columns.  b_lo_hi / b_lo_lo: low descriptor
+// words of the hi / lo B tiles; k-step = +2 (32 bytes).  acc0: accumulate flag of the very first MMA.
+__device__ __forceinline__ void umma_ts_chunk_3x(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_hi, uint32_t b_lo, uint32_t desc_hi,
+                                                 uint32_t idesc, uint32_t acc0) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 dh, dl;\n\t.reg .b32 ah, al, bh, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        // k-step 0
+        "mov.b64 dh, {%2, %4};\n\t mov.b64 dl, {%3, %4};\n\t add.u32 al, %1, 32;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dh, %5, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], dh, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dl, %5, t;\n\t"
+        // k-step 1
+        "add.u32 bh, %2, 2;\n\t add.u32 bl, %3, 2;\n\t add.u32 ah, %1, 8;\n\t add.u32 al, %1, 40;\n\t"
+        "mov.b64 dh, {bh, %4};\n\t mov.b64 dl, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], dh, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], dh, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], dl, %5, t;\n\t"
+        // k-step 2
+        "add.u32 bh, %2, 4;\n\t add.u32 bl, %3, 4;\n\t add.u32 ah, %1, 16;\n\t add.u32 al, %1, 48;\n\t"
+        "mov.b64 dh, {bh, %4};\n\t mov.b64 dl, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], dh, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], dh, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], dl, %5, t;\n\t"
+        // k-step 3
+        "add.u32 bh, %2, 6;\n\t add.u32 bl, %3, 6;\n\t add.u32 ah, %1, 24;\n\t add.u32 al, %1, 56;\n\t"
+        "mov.b64 dh, {bh, %4};\n\t mov.b64 dl, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], dh, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], dh, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], dl, %5, t;\n\t}"
+        :: "r"(tmem_d), "r"(tmem_a), "r"(b_hi), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc0) : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
@@ -130,7 +167,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 
 constexpr int kProdWarps = 16;
 constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kMmaThreads = kProdThreads + 32;
+constexpr int kMmaThreads = kProdThreads + 64;    // + issuer warp + weight-loader warp
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
