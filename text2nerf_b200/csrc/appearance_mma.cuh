@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                         const uint32_t bh = desc_lo(smb + L.b[bs]);
                         if (g == 2) {                       // basis: A from shared memory, N = 32 (B tile 32 rows)
                             const uint32_t ah = desc_lo(smb + L.a[it & 1]), al = ah + (kTileBytes >> 4), bl = bh + ((32 * 128) >> 4);
+                            if (terms == 7) umma_ss_chunk_3x(d, ah, al, bh, bl, kDescHi, idesc, c != 0);
+                            else
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
                                 umma_ss_elect(d, ah + 2 * kk, bh + 2 * kk, kDescHi, idesc, (c | kk) != 0);

@@ -131,6 +131,36 @@ __device__ __forceinline__ void umma_ts_chunk_3x(uint32_t tmem_d, uint32_t tmem_
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], dl, %5, t;\n\t}"
         :: "r"(tmem_d), "r"(tmem_a), "r"(b_hi), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc0) : "memory");
 }
+// Same for both operands in shared memory (basis chunks): a_hi / a_lo and b_hi / b_lo are the low descriptor words of the
+// hi / lo tiles; a k-step advances both by 2 (32 bytes).
+__device__ __forceinline__ void umma_ss_chunk_3x(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                 uint32_t desc_hi, uint32_t idesc, uint32_t acc0) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 ah, al, bh, bl;\n\t.reg .b32 x, y, z, w;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 ah, {%1, %5};\n\t mov.b64 al, {%2, %5};\n\t mov.b64 bh, {%3, %5};\n\t mov.b64 bl, {%4, %5};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %6, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %6, t;\n\t"
+        "add.u32 x, %1, 2;\n\t add.u32 y, %2, 2;\n\t add.u32 z, %3, 2;\n\t add.u32 w, %4, 2;\n\t"
+        "mov.b64 ah, {x, %5};\n\t mov.b64 al, {y, %5};\n\t mov.b64 bh, {z, %5};\n\t mov.b64 bl, {w, %5};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %6, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %6, t;\n\t"
+        "add.u32 x, %1, 4;\n\t add.u32 y, %2, 4;\n\t add.u32 z, %3, 4;\n\t add.u32 w, %4, 4;\n\t"
+        "mov.b64 ah, {x, %5};\n\t mov.b64 al, {y, %5};\n\t mov.b64 bh, {z, %5};\n\t mov.b64 bl, {w, %5};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %6, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %6, t;\n\t"
+        "add.u32 x, %1, 6;\n\t add.u32 y, %2, 6;\n\t add.u32 z, %3, 6;\n\t add.u32 w, %4, 6;\n\t"
+        "mov.b64 ah, {x, %5};\n\t mov.b64 al, {y, %5};\n\t mov.b64 bh, {z, %5};\n\t mov.b64 bl, {w, %5};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %6, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %6, t;\n\t}"
+        :: "r"(tmem_d), "r"(a_hi), "r"(a_lo), "r"(b_hi), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc0) : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
