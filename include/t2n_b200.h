@@ -247,6 +247,8 @@ int t2n_profile_enable(int on);
 /* Debug aid: with T2N_MMA_TRACE set in the environment the tensor-core appearance kernel's CTA 0 writes
  * 32 cycle counters (stage times, barrier waits); this copies them to the host.  Returns 32 or 0. */
 int t2n_debug_trace_read(long long* out32);
+/* Same, first n entries of the trace buffer (counters + the per-chunk timeline events of three iterations). */
+int t2n_debug_trace_read_n(long long* out, int n);
 int t2n_profile_read(int* ids, float* ms, int n);
 
 /* Test aids for the weight-gradient GEMM kernel (csrc/wgrad_mma.cuh), not part of the reference surface.

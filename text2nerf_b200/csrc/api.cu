@@ -119,6 +119,7 @@ struct Profiler {
 };
 Profiler g_prof;
 long long* g_trace = nullptr;
+constexpr int kTraceLen = 8192;   // 64 counters + timeline events of the forward appearance kernel
 
 AppArgs make_app_args(const T2NField* f, const T2NParams* p, const FieldDev& fd, const T2NBatch* b,
                       const T2NOutputs* out, const T2NScratch* s) {
@@ -188,6 +189,12 @@ int t2n_profile_enable(int on) {
 int t2n_debug_trace_read(long long* out32) {
     if (!g_trace || !out32) return 0;
     return cudaMemcpy(out32, g_trace, 32 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 32 : 0;
+}
+
+int t2n_debug_trace_read_n(long long* out, int n) {
+    if (!g_trace || !out || n <= 0) return 0;
+    if (n > kTraceLen) n = kTraceLen;
+    return cudaMemcpy(out, g_trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? n : 0;
 }
 
 int t2n_profile_read(int* ids, float* ms, int n) {
@@ -283,9 +290,11 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
             const char* benv = getenv("T2N_MMA_BACKOFF_NS");
             ma2.backoff_ns = benv ? (unsigned)atoi(benv) : 64u;
             if (getenv("T2N_MMA_TRACE")) {                       // debug cycle counters of CTA 0
-                if (!g_trace) cudaMalloc(&g_trace, 32 * sizeof(long long));
-                cudaMemsetAsync(g_trace, 0, 32 * sizeof(long long), st);
+                if (!g_trace) cudaMalloc(&g_trace, kTraceLen * sizeof(long long));
+                cudaMemsetAsync(g_trace, 0, kTraceLen * sizeof(long long), st);
                 ma2.trace = g_trace;
+                const char* denv = getenv("T2N_MMA_DBG");
+                ma2.dbg = denv ? atoi(denv) : 0;
             }
             const int smem_bytes = mma_smem_layout().total;
             if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
@@ -408,8 +417,8 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
             for (int i = 0; i < 3; ++i) { d.gap[i] = b.gap[i]; d.gal[i] = b.gal[i]; }
             d.g_b3 = grads->b3;
             if (getenv("T2N_BWD_TRACE")) {
-                if (!g_trace) cudaMalloc(&g_trace, 32 * sizeof(long long));
-                cudaMemsetAsync(g_trace, 0, 32 * sizeof(long long), st);
+                if (!g_trace) cudaMalloc(&g_trace, kTraceLen * sizeof(long long));
+                cudaMemsetAsync(g_trace, 0, kTraceLen * sizeof(long long), st);
                 d.trace = g_trace;
             }
             const int smem_bd = bwd_smem_layout().total;
@@ -458,8 +467,8 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
             b.skip_if_le = cap_rows;        // the FFMA kernel below only runs when the list overflowed the images
         }
         if (!use_mma && getenv("T2N_BWD_TRACE")) {
-            if (!g_trace) cudaMalloc(&g_trace, 32 * sizeof(long long));
-            cudaMemsetAsync(g_trace, 0, 32 * sizeof(long long), st);
+            if (!g_trace) cudaMalloc(&g_trace, kTraceLen * sizeof(long long));
+            cudaMemsetAsync(g_trace, 0, kTraceLen * sizeof(long long), st);
             b.trace = g_trace;
         }
         const AppBwdSmem BL = app_bwd_smem_layout(b.fw.n_app_total, b.fw.app_dim, b.fw.C, b.fw.Kp);

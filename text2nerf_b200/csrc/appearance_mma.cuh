@@ -7,23 +7,28 @@
 // tensor pipe far from saturated -- the producers (gathers, sin/cos) are the bound.
 //
 // One persistent CTA per SM walks the compacted app-sample list in tiles of 128 entries (= UMMA M).
-// All operands are K-major, 128-byte-swizzled tiles of 32 fp32 columns:
-//      A chunk  [128 points][32 k]  hi + lo  = 2 x 16 KB, produced by the CUDA cores (2-stage ring)
+// Operands are K-major chunks of 32 fp32 columns:
+//      A chunk  [128 points][32 k]  hi + lo, produced by the CUDA cores: into TMEM (decoder layers, TS-mode MMAs, ring of
+//               3 stages) or into 128-byte-swizzled shared memory (basis products, ring of 2 stages)
 //      B chunk  [N rows   ][32 k]  hi + lo, pre-swizzled images in global memory written by
-//               pack_mma_weights_kernel, fetched by ONE TMA bulk copy per chunk (2-stage ring)
-// and four "groups" of chunks run back to back per tile:
+//               pack_mma_weights_kernel, fetched by ONE TMA bulk copy per chunk (4-stage ring, dedicated loader warp)
+// and per tile four groups of work:
 //      S0  basis   : A = plane*line products (gather), 5 chunks, N = 32   -> D0  (TMEM cols 256..287)
 //      S1  layer 1 : A = decoder input columns, frequency-major (MmaRecipe), 13 chunks for the
 //                    configured head, N = 128                               -> D1  (cols 0..127)
 //      S2  layer 2 : A = relu(D1 + b1) read back from TMEM chunk by chunk, 4 chunks, N = 128
 //                                                                           -> D2  (cols 128..255)
 //      S3  layer 3 + sigmoid on the CUDA cores straight out of TMEM.
-// The stages of THREE consecutive tiles are software-pipelined -- iteration j runs S2(j-2), S1(j-1),
-// S0(j), S3(j-2) -- so no stage ever waits for the accumulator it has just fed: by the time a tile's
-// next stage starts, a whole other stage of another tile has been produced in between.  The producer
-// of chunk c+1 also overlaps the asynchronous MMAs of chunk c; mbarriers track "B landed" (TMA
-// complete_tx), "A written", "stage free" and "accumulator complete" (tcgen05.commit).
+// The groups of THREE consecutive tiles are software-pipelined: iteration j works on S2(j-2), S1(j-1), S0(j), S3(j-2).
+// Inside an iteration the producers follow a CHUNK PROGRAM (build_program) that all three roles read from shared memory:
+// the S2 chunks, then the S1 chunks with the S0 gather merged in between as "units" of 16 channels (half a chunk).  A
+// unit's 6 texel/tap loads per thread are issued one unit ahead and stay in flight (24 registers) while the thread
+// produces S1 chunks, so the L2 latency of the gather is hidden behind decoder work and the tensor pipe always has
+// queued MMAs; the slot/z/ray loads of the next tile are prefetched the same way two steps earlier.
+// mbarriers track "B landed" (TMA complete_tx), "A written" (16 warp arrivals), "chunk done" and "accumulator complete"
+// (tcgen05.commit); completion is in order, so the producers keep one monotone "done up to" index.
 #pragma once
+#include <type_traits>
 #include "umma.cuh"
 
 namespace t2n {
@@ -81,42 +86,53 @@ static __global__ void pack_mma_weights_kernel(const float* __restrict__ basis, 
     *reinterpret_cast<float4*>(dst_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-// issue the 3xTF32 MMAs of one K chunk: (Ahi,Bhi) (Alo,Bhi) (Ahi,Blo), 4 k-steps of 8 each
-__device__ __forceinline__ void issue_chunk(uint32_t a_stage, uint32_t b_stage, int b_rows, uint32_t tmem_d, uint32_t idesc,
-                                            bool first_chunk, int terms) {
-    const uint32_t a_hi = a_stage, a_lo = a_stage + kTileBytes;
-    const uint32_t b_hi = b_stage, b_lo = b_stage + (uint32_t)b_rows * 128;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        const uint64_t dah = umma_desc_sw128(a_hi + kk * 32), dal = umma_desc_sw128(a_lo + kk * 32);
-        const uint64_t dbh = umma_desc_sw128(b_hi + kk * 32), dbl = umma_desc_sw128(b_lo + kk * 32);
-        umma_tf32(tmem_d, dah, dbh, idesc, !(first_chunk && kk == 0));
-        if (terms & 2) umma_tf32(tmem_d, dal, dbh, idesc, true);
-        if (terms & 4) umma_tf32(tmem_d, dah, dbl, idesc, true);
+// ---- the chunk program -----------------------------------------------------------------------------------------------
+// Steps of one pipeline iteration, in producer order.  kind in the low 3 bits, index in the high 5.
+//   Pre  (tile j)   load the list slot of this thread's sample
+//   S2 c (tile j-2) layer-2 A chunk c
+//   Ray  (tile j)   load z and the ray of the slot
+//   S1 c (tile j-1) layer-1 A chunk c (c = 0 also moves the feature D0 -> shared memory and seeds sin/cos)
+//   Pro  (tile j)   sample geometry, base vector tail, loads of gather unit 0
+//   U k  (tile j)   gather unit k (16 product channels): consume the prefetched taps, prefetch unit k+1, write half a
+//                   basis A chunk; odd k publishes chunk k/2
+//   S3   (tile j-2) layer 3 + sigmoid
+// Only S2 / S1 / odd-U steps are chunks (B copy, MMAs); the issuer and the loader skip the rest.
+enum : int { kStepS2 = 0, kStepS1 = 1, kStepU = 2, kStepPre = 3, kStepRay = 4, kStepPro = 5, kStepS3 = 6 };
+__device__ inline int build_program(uint8_t* prog, int nk0, int nk1, int nk2) {
+    int n = 0;
+    auto put = [&](int kind, int idx) { prog[n++] = (uint8_t)(kind | (idx << 3)); };
+    put(kStepPre, 0);
+    const int early = nk2 < 2 ? nk2 : 2;
+    for (int c = 0; c < early; ++c) put(kStepS2, c);
+    put(kStepRay, 0);
+    for (int c = early; c < nk2; ++c) put(kStepS2, c);
+    put(kStepS1, 0);
+    put(kStepPro, 0);
+    const int T = nk1 - 1, Un = 2 * nk0;
+    int ts = 0;
+    for (int k = 0; k < Un; ++k) {
+        const int target = ((k + 1) * T + Un - 1) / Un;
+        while (ts < target) { put(kStepS1, 1 + ts); ++ts; }
+        put(kStepU, k);
     }
+    while (ts < T) { put(kStepS1, 1 + ts); ++ts; }
+    put(kStepS3, 0);
+    return n;
 }
-// same with the A chunk in tensor memory (stage = 64 columns: hi | lo)
-__device__ __forceinline__ void issue_chunk_ts(uint32_t a_tmem, uint32_t b_stage, uint32_t tmem_d, uint32_t idesc,
-                                               bool first_chunk, int terms) {
-    const uint32_t b_hi = b_stage, b_lo = b_stage + 128u * 128u;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        const uint64_t dbh = umma_desc_sw128(b_hi + kk * 32), dbl = umma_desc_sw128(b_lo + kk * 32);
-        umma_tf32_ts(tmem_d, a_tmem + kk * 8, dbh, idesc, !(first_chunk && kk == 0));
-        if (terms & 2) umma_tf32_ts(tmem_d, a_tmem + 32 + kk * 8, dbh, idesc, true);
-        if (terms & 4) umma_tf32_ts(tmem_d, a_tmem + kk * 8, dbl, idesc, true);
-    }
-}
+
+// stage offsets as arithmetic (indexing MmaSmem::a / ::b with a runtime index would put the struct in local memory)
+__device__ __forceinline__ uint32_t a_stage_off(uint32_t i) { return i * (uint32_t)kStageA; }
+__device__ __forceinline__ uint32_t b_stage_off(uint32_t i) { return 2u * (uint32_t)kStageA + i * (uint32_t)kStageB; }
 
 // Requirements (checked by the host): MLP shading, feature_c == 128, app_dim <= 29, every n_app[i] a
 // multiple of 16, sum(n_app) <= 160.
 //
 // Warp roles: warps 0..15 (512 threads) are PRODUCERS/EPILOGUES -- they build the A chunks (gather,
-// decoder columns, relu(D1+b1)) and read the accumulators; warp 16 lane 0 is the ISSUER -- it streams
-// the B chunks with TMA bulk copies and issues every tcgen05.mma.  The two sides only meet on
-// mbarriers (a_full: 16 warp arrivals, b_full: TMA bytes, free/acc: tcgen05.commit) and both walk the
-// same chunk sequence, so there is no CTA-wide barrier in the chunk loops.
+// decoder columns, relu(D1+b1)) and read the accumulators; warp 16 is the ISSUER of every tcgen05.mma, warp 17 the
+// weight LOADER (TMA bulk copies).  The roles only meet on mbarriers (a_full: 16 warp arrivals, b_full: TMA bytes,
+// done/acc: tcgen05.commit) and all walk the same chunk program, so there is no CTA-wide barrier in the loop.
 static_assert(kNB == 4, "bar_done ring assumes a 4-deep B ring");
+template <bool TR>
 __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const __grid_constant__ AppMmaArgs args) {
     extern __shared__ uint8_t smem_raw[];
     const AppArgs& a = args.fw;
@@ -135,12 +151,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
     float* part = reinterpret_cast<float*>(sm + L.part);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint64_t* bar_bfull = bars;         // [kNB] B chunk landed (TMA complete_tx)
-    uint64_t* bar_done = bars + 4;      // [4] MMAs of chunk it (slot it % 4) have completed (tcgen05.commit): frees A stage
-                                        //     it & 1 for the producers and B stage it % kNB for the weight prefetcher
-    uint64_t* bar_afull = bars + 8;     // [4] A chunk written by all 16 producer warps (ring of 4: producers run up to 3 chunks ahead)
+    uint64_t* bar_done = bars + 4;      // [4] MMAs of chunk it (slot it % 4) have completed (tcgen05.commit): frees the A stage
+                                        //     for the producers and B stage it % kNB for the loader
+    uint64_t* bar_afull = bars + 8;     // [4] A chunk written by all 16 producer warps (producers run up to 3 chunks ahead)
     uint64_t* bar_acc = bars + 12;      // [3] accumulator D0 / D1 / D2 of a tile complete (tcgen05.commit)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
+    uint8_t* prog = sm + L.prog;
+    int* n_prog_s = reinterpret_cast<int*>(sm + L.prog + kMaxProg);       // [0] n_prog, [1] unit mask of the merged part
+    int* geo = reinterpret_cast<int*>(sm + L.geo);                        // [128][6] texel index / fraction per axis of the tile's samples
 
+    const int nk0 = P.basis_chunks, nk1 = P.w1_chunks, nk2 = P.w2_chunks;
     for (int i = tid; i < 128; i += kMmaThreads) { b1s[i] = __ldg(a.b1 + i); b2s[i] = __ldg(a.b2 + i); }
     for (int i = tid; i < 3 * 128; i += kMmaThreads) w3s[i] = __ldg(a.w3 + i);
     if (tid < 3) b3s[tid] = __ldg(a.b3 + tid);
@@ -149,6 +169,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
         for (int i = 0; i < 4; ++i) mbar_init(bar_afull + i, kProdWarps);
         for (int i = 0; i < 3; ++i) mbar_init(bar_acc + i, 1);
         mbar_fence_init();
+        const int np = build_program(prog, nk0, nk1, nk2);
+        n_prog_s[0] = np;
+        unsigned um = 0;                    // bit s: step merged_begin + s is a gather unit (else an S1 chunk)
+        for (int q = nk2 + 4; q < np - 1; ++q) if ((prog[q] & 7) == kStepU) um |= 1u << (q - (nk2 + 4));
+        n_prog_s[1] = (int)um;
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
@@ -158,17 +183,24 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const int n_prog = n_prog_s[0];
 
-    const int nk0 = P.basis_chunks, nk1 = P.w1_chunks, nk2 = P.w2_chunks;
     int n_tiles = 0;
     for (int tile = blockIdx.x; tile * kMmaM < total; tile += gridDim.x) ++n_tiles;
 
-    // the chunk sequence all roles walk: iteration j = [S2 of tile j-2][S1 of tile j-1][S0 of tile j]
-    auto group_valid = [&](int j, int g) {
-        const int t = j - (2 - g);      // g=0 -> tile j-2, g=1 -> tile j-1, g=2 -> tile j
+    // timeline events of CTA 0 (trace instantiation only): ev[warp][iteration - kTrJ0][chunk of the iteration][kind]
+    constexpr int kTrJ0 = 500, kTrNJ = 3, kTrCh = 24;
+    auto ev = [&](int j, int ci, int k) {
+        if (TR && args.trace != nullptr && blockIdx.x == 0 && lane == 0 && j >= kTrJ0 && j < kTrJ0 + kTrNJ && ci < kTrCh)
+            args.trace[64 + ((warp * kTrNJ + (j - kTrJ0)) * kTrCh + ci) * 4 + k] = clock64();
+    };
+
+    // tile a step of iteration j works on: S2 / S3 -> j-2, S1 -> j-1, everything else -> j
+    auto step_ok = [&](int j, int kind) {
+        const int t = j - ((kind == kStepS2 || kind == kStepS3) ? 2 : (kind == kStepS1 ? 1 : 0));
         return t >= 0 && t < n_tiles;
     };
-    auto group_len = [&](int g) { return g == 0 ? nk2 : (g == 1 ? nk1 : nk0); };
+    auto is_chunk = [&](int kind, int idx) { return kind < kStepU || (kind == kStepU && (idx & 1)); };
 
     if (warp == kProdWarps + 1) {
         // =========================== WEIGHT LOADER ===========================
@@ -179,18 +211,19 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             const uint32_t bars_addr = smb + L.bars;
             uint32_t loaded = 0;
             for (int j = 0; j < n_tiles + 2; ++j)
-                for (int g = 0; g < 3; ++g) {
-                    if (!group_valid(j, g)) continue;
-                    const int len = group_len(g);
-                    for (int c = 0; c < len; ++c, ++loaded) {
-                        const uint32_t bs = loaded % kNB;
-                        if (loaded >= kNB) mbar_wait(bar_done + bs, ((loaded / kNB) - 1) & 1);
-                        const float* src; uint32_t bytes;
-                        if (g == 2) { src = args.pack + P.basis_off + (size_t)c * 2 * 32 * 32; bytes = 2 * 32 * 128; }
-                        else if (g == 1) { src = args.pack + P.w1_off + (size_t)c * 2 * 128 * 32; bytes = 2 * kTileBytes; }
-                        else { src = args.pack + P.w2_off + (size_t)c * 2 * 128 * 32; bytes = 2 * kTileBytes; }
-                        tma_load_elect(smb + L.b[bs], src, bytes, bars_addr + 8 * bs);
-                    }
+                for (int s = 0, ci = 0; s < n_prog; ++s) {
+                    const int kind = prog[s] & 7, idx = prog[s] >> 3;
+                    if (!is_chunk(kind, idx) || !step_ok(j, kind)) continue;
+                    const uint32_t bs = loaded % kNB;
+                    if (loaded >= kNB) mbar_wait(bar_done + bs, ((loaded / kNB) - 1) & 1);
+                    ev(j, ci++, 0);
+                    const float* src; uint32_t bytes;
+                    if (kind == kStepU) { src = args.pack + P.basis_off + (size_t)(idx >> 1) * 2 * 32 * 32; bytes = 2 * 32 * 128; }
+                    else if (kind == kStepS1) { src = args.pack + P.w1_off + (size_t)idx * 2 * 128 * 32; bytes = 2 * kTileBytes; }
+                    else { src = args.pack + P.w2_off + (size_t)idx * 2 * 128 * 32; bytes = 2 * kTileBytes; }
+                    if (TR && (args.dbg & 4)) bytes >>= 1;      // debug: hi image only
+                    tma_load_elect(smb + b_stage_off(bs), src, bytes, bars_addr + 8 * bs);
+                    ++loaded;
                 }
         }
     } else if (warp == kProdWarps) {
@@ -201,141 +234,219 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             const uint32_t smb = __shfl_sync(T2N_FULL, sm_addr, 0);
             const uint32_t bars_addr = smb + L.bars;
             const int terms = args.terms;
-            uint32_t it = 0;
-            const bool tr = args.trace != nullptr && blockIdx.x == 0 && lane == 0;
-            long long w_af = 0, w_bf = 0, t_is = 0, t_pf = 0, t0i = clock64();
+            uint32_t it = 0, n0 = 0;
+            long long w_af = 0, w_bf = 0, t_is = 0, t0i = TR ? clock64() : 0;
             for (int j = 0; j < n_tiles + 2; ++j)
-                for (int g = 0; g < 3; ++g) {
-                    if (!group_valid(j, g)) continue;
-                    const int len = group_len(g);
-                    const uint32_t d = tm + (g == 0 ? kColD2 : (g == 1 ? kColD1 : kColD0));
-                    const uint32_t idesc = g == 2 ? idesc32 : idesc128;
-                    for (int c = 0; c < len; ++c, ++it) {
-                        const uint32_t bs = it % kNB;
-                        long long c0 = clock64();
-                        mbar_wait(bar_bfull + bs, (it / kNB) & 1);
-                        long long c1 = clock64();
-                        mbar_wait(bar_afull + (it & 3), (it >> 2) & 1);
-                        long long c2 = clock64();
-                        tc_fence_after();
-                        const uint32_t bh = desc_lo(smb + L.b[bs]);
-                        if (g == 2) {                       // basis: A from shared memory, N = 32 (B tile 32 rows)
-                            const uint32_t ah = desc_lo(smb + L.a[it & 1]), al = ah + (kTileBytes >> 4), bl = bh + ((32 * 128) >> 4);
-                            if (terms == 7) umma_ss_chunk_3x(d, ah, al, bh, bl, kDescHi, idesc, c != 0);
-                            else
+                for (int s = 0, ci = 0; s < n_prog; ++s) {
+                    const int kind = prog[s] & 7, idx = prog[s] >> 3;
+                    if (!is_chunk(kind, idx) || !step_ok(j, kind)) continue;
+                    const int c = kind == kStepU ? (idx >> 1) : idx;
+                    const int len = kind == kStepS2 ? nk2 : (kind == kStepS1 ? nk1 : nk0);
+                    const uint32_t d = tm + (kind == kStepS2 ? kColD2 : (kind == kStepS1 ? kColD1 : kColD0));
+                    const uint32_t bs = it % kNB;
+                    long long c0 = 0, c1 = 0, c2 = 0;
+                    if (TR) c0 = clock64();
+                    mbar_wait(bar_bfull + bs, (it / kNB) & 1);
+                    if (TR) c1 = clock64();
+                    ev(j, ci, 0);
+                    mbar_wait(bar_afull + (it & 3), (it >> 2) & 1);
+                    if (TR) c2 = clock64();
+                    ev(j, ci, 1);
+                    tc_fence_after();
+                    const uint32_t bh = desc_lo(smb + b_stage_off(bs));
+                    if (TR && (args.dbg & 2)) {
+                    } else if (kind == kStepU) {               // basis: A from shared memory, N = 32 (B tile 32 rows)
+                        const uint32_t ah = desc_lo(smb + a_stage_off(n0 & 1)), al = ah + (kTileBytes >> 4), bl = bh + ((32 * 128) >> 4);
+                        ++n0;
+                        if (terms == 7) umma_ss_chunk_3x(d, ah, al, bh, bl, kDescHi, idesc32, c != 0);
+                        else
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
-                                umma_ss_elect(d, ah + 2 * kk, bh + 2 * kk, kDescHi, idesc, (c | kk) != 0);
-                                if (terms & 2) umma_ss_elect(d, al + 2 * kk, bh + 2 * kk, kDescHi, idesc, 1);
-                                if (terms & 4) umma_ss_elect(d, ah + 2 * kk, bl + 2 * kk, kDescHi, idesc, 1);
+                                umma_ss_elect(d, ah + 2 * kk, bh + 2 * kk, kDescHi, idesc32, (c | kk) != 0);
+                                if (terms & 2) umma_ss_elect(d, al + 2 * kk, bh + 2 * kk, kDescHi, idesc32, 1);
+                                if (terms & 4) umma_ss_elect(d, ah + 2 * kk, bl + 2 * kk, kDescHi, idesc32, 1);
                             }
-                        } else {                            // decoder layers: A from tensor memory (hi | lo), N = 128
-                            const uint32_t ta = tm + kColA + 64 * (it % kTmemAStages), bl = bh + (kTileBytes >> 4);
-                            if (terms == 7) umma_ts_chunk_3x(d, ta, bh, bl, kDescHi, idesc, c != 0);
-                            else
+                    } else {                            // decoder layers: A from tensor memory (hi | lo), N = 128
+                        const uint32_t ta = tm + kColA + 64 * (it % kTmemAStages), bl = bh + (kTileBytes >> 4);
+                        if (terms == 7) umma_ts_chunk_3x(d, ta, bh, bl, kDescHi, idesc128, c != 0);
+                        else
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
-                                umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc, (c | kk) != 0);
-                                if (terms & 2) umma_ts_elect(d, ta + 32 + 8 * kk, bh + 2 * kk, kDescHi, idesc, 1);
-                                if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc, 1);
+                                umma_ts_elect(d, ta + 8 * kk, bh + 2 * kk, kDescHi, idesc128, (c | kk) != 0);
+                                if (terms & 2) umma_ts_elect(d, ta + 32 + 8 * kk, bh + 2 * kk, kDescHi, idesc128, 1);
+                                if (terms & 4) umma_ts_elect(d, ta + 8 * kk, bl + 2 * kk, kDescHi, idesc128, 1);
                             }
-                        }
-                        umma_commit_elect(bars_addr + 8 * (4 + bs));               // bar_done[it % 4]
-                        if (c == len - 1) umma_commit_elect(bars_addr + 8 * (12 + (2 - g)));   // bar_acc: g=0 -> D2, 1 -> D1, 2 -> D0
-                        long long c3 = clock64();
-                        long long c4 = c3;
-                        w_bf += c1 - c0; w_af += c2 - c1; t_is += c3 - c2; t_pf += c4 - c3;
                     }
+                    umma_commit_elect(bars_addr + 8 * (4 + bs));                                    // bar_done[it % 4]
+                    if (c == len - 1)                                                               // bar_acc: D0 / D1 / D2
+                        umma_commit_elect(bars_addr + 8 * (12 + (kind == kStepS2 ? 2 : (kind == kStepS1 ? 1 : 0))));
+                    if (TR) { const long long c3 = clock64(); w_bf += c1 - c0; w_af += c2 - c1; t_is += c3 - c2; }
+                    ev(j, ci++, 2);
+                    ++it;
                 }
-            if (tr) {
+            if (TR && args.trace != nullptr && blockIdx.x == 0 && lane == 0) {
                 args.trace[16] = clock64() - t0i; args.trace[17] = w_bf; args.trace[18] = w_af; args.trace[19] = t_is;
-                args.trace[20] = t_pf; args.trace[21] = it; args.trace[22] = n_tiles;
+                args.trace[21] = it; args.trace[22] = n_tiles;
             }
         }
     } else {
         // =========================== PRODUCERS ===========================
-        const bool tr = args.trace != nullptr && blockIdx.x == 0 && tid == 0;
-        long long tS[4] = {0, 0, 0, 0}, wAcc[3] = {0, 0, 0}, wSt[3] = {0, 0, 0}, t0p = clock64();
-        int cur_stage = 0;
-        uint32_t it = 0;        // chunks produced so far by this CTA (ring position)
-        auto stage_acquire = [&](uint32_t i, bool smem_stage = false) {
-            const long long c0 = clock64();
-            // shared-memory A stages (basis chunks) form a ring of 2, TMEM A stages (decoder layers) a ring of kTmemAStages:
-            // the stage is free once the chunk that last used it (at most `back` chunks ago) has completed
-            const uint32_t back = smem_stage ? 2u : (uint32_t)kTmemAStages;
-            if (i >= back) mbar_wait_backoff(bar_done + ((i - back) & 3), ((i - back) >> 2) & 1, args.backoff_ns);
-            wSt[cur_stage] += clock64() - c0;
+        long long tK[7] = {0, 0, 0, 0, 0, 0, 0}, w_acc = 0, w_done = 0, t0p = TR ? clock64() : 0;
+        int it = 0;                 // chunks published so far by this CTA
+        int n0 = 0;                 // basis (shared-memory A) chunks published so far
+        int done_known = -1;        // every chunk <= done_known has completed (completion is in order)
+        int s0_last0 = -1, s0_last1 = -1;   // chunk index of the last user of shared-memory A stage 0 / 1
+        // Wait until chunk p has completed.  Requires p >= it - 4 (the slot's phase must not have been reused), which
+        // holds for every caller: TS stages wait for it - 3, basis stages for the basis chunk two back.
+        auto wait_done = [&](int p) {
+            if (p > done_known) {
+                long long c0 = 0;
+                if (TR) c0 = clock64();
+                mbar_wait_backoff(bar_done + (p & 3), (uint32_t)(p >> 2) & 1u, args.backoff_ns);
+                if (TR) w_done += clock64() - c0;
+                done_known = p;
+            }
         };
-        auto stage_publish = [&](uint32_t i) {          // generic-proxy writes -> async proxy, then one arrival per warp
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_afull + (i & 3));
-        };
-        auto stage_publish_tmem = [&](uint32_t i) {     // tcgen05.st writes complete, then one arrival per warp
+        int tr_j = 0, tr_ci = 0;
+        auto publish_tmem = [&]() {     // tcgen05.st writes complete, then one arrival per warp
+            ev(tr_j, tr_ci, 1);
             tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_afull + (i & 3));
+            ev(tr_j, tr_ci, 3);
+            tc_fence_before();              // (tcgen05.wait::st is .sync.aligned: the warp is converged here)
+            if (lane == 0) mbar_arrive(bar_afull + (it & 3));
+            ev(tr_j, tr_ci++, 2);
+            ++it;
         };
         auto acc_wait = [&](int which, int local_tile) {     // accumulator `which` (0=D0,1=D1,2=D2) of the CTA's n-th tile
-            const long long c0 = clock64();
+            long long c0 = 0;
+            if (TR) c0 = clock64();
             mbar_wait_backoff(bar_acc + which, local_tile & 1, args.backoff_ns);
-            wAcc[which] += clock64() - c0;
+            if (TR) w_acc += clock64() - c0;
             tc_fence_after();
         };
-        const int row = tid >> 2, sub = tid & 3;            // S0 mapping: 4 threads per point, 8 channels each
-        const int erow = 32 * (warp & 3) + lane;            // epilogue mapping: TMEM lane = row
+        const int row = tid >> 2, sub = tid & 3;            // gather mapping: 4 threads per point, 4 channels each per unit
+        const int erow = 32 * (warp & 3) + lane;            // epilogue / S1 mapping: TMEM lane = row
         const int eq = warp >> 2;                           // column quarter handled by this warp
         const uint32_t tmem_lane = (uint32_t)(32 * (warp & 3)) << 16;
-        const int m1 = tid & 127, ph = tid >> 7;            // S1 mapping: row, entry group
-        // S1: the 8 decoder entries this thread owns: 4ph..4ph+3 (first half chunk) and 16+4ph.. (second)
-        int ent_src[8], ent_nf[8];
+        const int G0 = a.f.G[0], G1 = a.f.G[1], G2 = a.f.G[2];
+
+        float sn[8], cs[8];                                 // S1: (sin, cos) of the 8 entries this thread owns
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int e = (q < 4) ? (4 * ph + q) : (16 + 4 * ph + (q - 4));
-            ent_src[q] = args.pe_src[e];
-            ent_nf[q] = args.pe_nf[e];
-        }
-        int id_src[8];
+        for (int q = 0; q < 8; ++q) { sn[q] = 0.f; cs[q] = 1.f; }
+        // gather state of tile j
+        bool live = false, pf_have = false;
+        int slot = 0;
+        float gz = 0.f, ro0 = 0.f, ro1 = 0.f, ro2 = 0.f, rd0 = 0.f, rd1 = 0.f, rd2 = 0.f;
+        float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f), pf1 = pf0, pf2 = pf0, pf3 = pf0, pf4 = pf0, pf5 = pf0;
+        float w_nw = 0.f, w_ne = 0.f, w_sw = 0.f, w_se = 0.f, w_z0 = 0.f, w_z1 = 0.f;
+        const float* pl_ptr = a.ap[0];      // footprint of the current plane: texel (y0, x0) minus the plane's channel offset
+        const float* ln_ptr = a.al[0];
+        int pl_dx = 0, pl_dy = 0, ln_dz = 0;
+
+        // Issue the 6 loads (4 plane texels, 2 line taps; 4 channels each) of gather unit k.  The footprint of the unit's plane
+        // (texel pointer, +x / +y steps, the four bilinear weights, line pointer, step and weights) is rebuilt only when the
+        // unit enters a new plane (every third unit for 48-channel planes): a unit then costs six address adds.
+        auto unit_loads = [&](int k) {
+            const int c16 = k * 16;
+            const int i = c16 >= a.aoff[2] ? 2 : (c16 >= a.aoff[1] ? 1 : 0);       // warp-uniform: n_app[i] % 16 == 0
+            const int comp0 = c16 + sub * 4;
+            pf_have = live && comp0 < a.n_app_total;
+            if (live && (k == 0 || c16 == a.aoff[i])) {
+                // plane i spans axes (a0, a1) = (0,1),(0,2),(1,2); its line runs along 2 - i.  The sample's texel index and
+                // fraction per axis were parked in shared memory by Pro (six registers less in the merged loop).
+                const int* gr = geo + row * 6;
+                const int a0 = i == 2 ? 1 : 0, a1 = i == 0 ? 1 : 2, av = 2 - i;
+                const Axis X = make_axis(gr[a0], __int_as_float(gr[3 + a0]), i == 2 ? G1 : G0);
+                const Axis Y = make_axis(gr[a1], __int_as_float(gr[3 + a1]), i == 0 ? G1 : G2);
+                const Axis Z = make_axis(gr[av], __int_as_float(gr[3 + av]), i == 0 ? G2 : (i == 1 ? G1 : G0));
+                const int C = a.ac[i], W = i == 2 ? G1 : G0;
+                w_nw = __fmul_rn(X.w0, Y.w0); w_ne = __fmul_rn(X.w1, Y.w0);
+                w_sw = __fmul_rn(X.w0, Y.w1); w_se = __fmul_rn(X.w1, Y.w1);
+                w_z0 = Z.w0; w_z1 = Z.w1;
+                pl_ptr = a.ap[i] + ((size_t)Y.c0 * W + X.c0) * C - a.aoff[i];
+                pl_dx = (X.c1 - X.c0) * C;
+                pl_dy = (Y.c1 - Y.c0) * W * C;
+                ln_ptr = a.al[i] + Z.c0 * C - a.aoff[i];
+                ln_dz = (Z.c1 - Z.c0) * C;
+            }
+            if (pf_have && !(TR && (args.dbg & 1))) {
+                const float* pp = pl_ptr + comp0;
+                const float* lp = ln_ptr + comp0;
+                pf0 = ldg4(pp);
+                pf1 = ldg4(pp + pl_dx);
+                pf2 = ldg4(pp + pl_dy);
+                pf3 = ldg4(pp + pl_dx + pl_dy);
+                pf4 = ldg4(lp);
+                pf5 = ldg4(lp + ln_dz);
+            }
+        };
+
+        // The head of an iteration is straight-line code in the order build_program() emits it (Pre, S2 [0, early), Ray,
+        // S2 [early, nk2), S1 chunk 0, Pro); the merged S1 / gather-unit part is read from the program; S3 closes the
+        // iteration.  Keeping S2 / S3 / S1 chunk 0 out of the merged loop keeps the prefetched taps (24 registers) and the
+        // sin/cos state dead while the TMEM epilogues need their registers.
+        const int n_merged = n_prog - 1 - (nk2 + 4);   // program minus Pre, Ray, S1 chunk 0, Pro, the nk2 S2 chunks and S3
+        const unsigned umask = (unsigned)n_prog_s[1];
+        const int early = nk2 < 2 ? nk2 : 2;
+        auto tmark = [&](int kind, long long& ts0) {
+            if (TR) { const long long now = clock64(); tK[kind] += now - ts0; ts0 = now; }
+        };
+        auto s2_chunk = [&](int j, int c) {
+            ev(tr_j, tr_ci, 0);
+            if (c == 0) acc_wait(1, j - 2);
+            const int e_row = (blockIdx.x + (j - 2) * gridDim.x) * kMmaM + erow;
+            uint32_t v[8];
+            const int col0 = c * 32 + eq * 8;
+            tmem_ld8(tmem + tmem_lane + kColD1 + col0, v);
+            float h[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) id_src[q] = args.ident_src[8 * ph + q];
+            for (int q = 0; q < 8; ++q) h[q] = fmaxf(__uint_as_float(v[q]) + b1s[col0 + q], 0.f);
+            if (args.h1_img != nullptr && e_row < args.act_rows)        // operand image for the backward (all 128 rows)
+                img_store8(args.h1_img + (size_t)(e_row >> 7) * img_tile_bytes(4), 4, erow, c, eq, h);
+            wait_done(it - kTmemAStages);
+            st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), eq * 8, h);
+            publish_tmem();
+        };
 
         for (int j = 0; j < n_tiles + 2; ++j) {
-            // ================= S2(j-2): relu(D1 + b1) -> layer 2 =================
-            long long ts0 = clock64();
-            if (j - 2 >= 0 && j - 2 < n_tiles) {
-                cur_stage = 0;
-                acc_wait(1, j - 2);
-                const int e_row = (blockIdx.x + (j - 2) * gridDim.x) * kMmaM + erow;
-                for (int c = 0; c < nk2; ++c, ++it) {
-                    uint32_t v[8];
-                    const int col0 = c * 32 + eq * 8;
-                    tmem_ld8(tmem + tmem_lane + kColD1 + col0, v);
-                    float h[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) h[q] = fmaxf(__uint_as_float(v[q]) + b1s[col0 + q], 0.f);
-                    if (args.h1_img != nullptr && e_row < args.act_rows)        // operand image for the backward (all 128 rows)
-                        img_store8(args.h1_img + (size_t)(e_row >> 7) * img_tile_bytes(4), 4, erow, c, eq, h);
-                    stage_acquire(it);
-                    st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), eq * 8, h);
-                    stage_publish_tmem(it);
-                }
+            const bool ok0 = j < n_tiles, ok1 = j >= 1 && j - 1 < n_tiles, ok2 = j >= 2 && j - 2 < n_tiles;
+            tr_j = j; tr_ci = 0;
+            long long ts0 = 0;
+            if (TR) ts0 = clock64();
+            // ---- Pre(j): list slot of this thread's sample
+            if (ok0) {
+                const int e = (blockIdx.x + j * gridDim.x) * kMmaM + row;
+                live = e < total;
+                if (live) slot = __ldg(a.slots + e);
             }
-            // ================= S1(j-1): feature from D0, decoder input columns -> layer 1 =================
-            long long ts1 = clock64(); tS[2] += ts1 - ts0;
-            if (j - 1 >= 0 && j - 1 < n_tiles) {
-                cur_stage = 1;
+            tmark(kStepPre, ts0);
+            // ---- S2(j-2), first chunks
+            if (ok2) for (int c = 0; c < early; ++c) s2_chunk(j, c);
+            tmark(kStepS2, ts0);
+            // ---- Ray(j): z and the ray of the slot
+            if (ok0 && live) {
+                const int r = slot / a.S;
+                gz = __ldg(a.z_vals + slot);
+                const float2* rp = reinterpret_cast<const float2*>(a.rays + (size_t)r * 6);
+                const float2 u0 = __ldg(rp), u1 = __ldg(rp + 1), u2 = __ldg(rp + 2);
+                ro0 = u0.x; ro1 = u0.y; ro2 = u1.x; rd0 = u1.y; rd1 = u2.x; rd2 = u2.y;
+            }
+            tmark(kStepRay, ts0);
+            if (ok2) for (int c = early; c < nk2; ++c) s2_chunk(j, c);
+            tmark(kStepS2, ts0);
+            // ---- S1(j-1) chunk 0: feature out of D0 -> base vector; identity columns; seed the sin/cos recurrences
+            if (ok1) {
+                ev(tr_j, tr_ci, 0);
                 acc_wait(0, j - 1);
                 if (warp < 4) {
                     uint32_t v[16];
-                    float* brow = base + erow * kBaseStride;
+                    float* bw = base + erow * kBaseStride;
                     tmem_ld16(tmem + tmem_lane + kColD0, v);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) if (q < a.app_dim) brow[q] = __uint_as_float(v[q]);
+                    for (int q = 0; q < 16; ++q) if (q < a.app_dim) bw[q] = __uint_as_float(v[q]);
                     tmem_ld16(tmem + tmem_lane + kColD0 + 16, v);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) if (16 + q < a.app_dim) brow[16 + q] = __uint_as_float(v[q]);
+                    for (int q = 0; q < 16; ++q) if (16 + q < a.app_dim) bw[16 + q] = __uint_as_float(v[q]);
                     const int e_feat = (blockIdx.x + (j - 1) * gridDim.x) * kMmaM + erow;
                     if (args.feat != nullptr && e_feat < args.act_rows) {       // feature vector for the backward's PE chain
                         float4* dst = reinterpret_cast<float4*>(args.feat + (size_t)e_feat * 32);
@@ -343,80 +454,45 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                         for (int q4 = 0; q4 < 8; ++q4) {
                             float f4v[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) f4v[u] = (4 * q4 + u < a.app_dim) ? brow[4 * q4 + u] : 0.f;
+                            for (int u = 0; u < 4; ++u) f4v[u] = (4 * q4 + u < a.app_dim) ? bw[4 * q4 + u] : 0.f;
                             dst[q4] = make_float4(f4v[0], f4v[1], f4v[2], f4v[3]);
                         }
                     }
                 }
                 tc_fence_before();
                 producers_sync();
-                const float* brow = base + m1 * kBaseStride;
-                // chunk 0: identity columns 8ph .. 8ph+7
-                {
-                    float c0[8];
+                const float* brow = base + erow * kBaseStride;
+                float cols[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) c0[q] = brow[id_src[q]];
-                    stage_acquire(it);
-                    st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), 8 * ph, c0);
-                    stage_publish_tmem(it);
-                    ++it;
-                }
-                // frequency blocks: one precise sincosf per owned entry, then angle doubling
-                float sn[8], cs[8];
+                for (int q = 0; q < 8; ++q) cols[q] = brow[args.ident_src[8 * eq + q]];
+                wait_done(it - kTmemAStages);
+                st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), 8 * eq, cols);
+                publish_tmem();
+                // entries this thread owns: 4eq..4eq+3 (first half chunk of a frequency) and 16+4eq.. (second)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
+                    const int e = (q < 4) ? (4 * eq + q) : (16 + 4 * eq + (q - 4));
                     sn[q] = 0.f; cs[q] = 1.f;
-                    if (ent_nf[q] > 0) sincosf(brow[ent_src[q]], &sn[q], &cs[q]);
-                }
-                for (int f = 0; f < args.n_freq; ++f) {
-                    if (f > 0) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float s2 = 2.f * sn[q];
-                            const float ns = s2 * cs[q];
-                            cs[q] = fmaf(-s2, sn[q], 1.f);
-                            sn[q] = ns;
-                        }
-                    }
-                    for (int h = 0; h < args.pe_chunks; ++h, ++it) {
-                        float cols[8];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            cols[2 * q] = h ? sn[4 + q] : sn[q];
-                            cols[2 * q + 1] = h ? cs[4 + q] : cs[q];
-                        }
-                        stage_acquire(it);
-                        st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), 8 * ph, cols);
-                        stage_publish_tmem(it);
-                    }
+                    if (args.pe_nf[e] > 0) sincosf(brow[args.pe_src[e]], &sn[q], &cs[q]);
                 }
             }
-            // ================= S0(j): gather -> products -> basis MMA =================
-            long long ts2 = clock64(); tS[1] += ts2 - ts1;
-            if (j < n_tiles) {
-                cur_stage = 2;
-                // heads with view-direction columns read base[viewdir] in S1; do not let fast warps
-                // overwrite it with the next tile's directions before everybody is through S1
+            tmark(kStepS1, ts0);
+            // ---- Pro(j): sample geometry, tail of the base vector, loads of gather unit 0
+            if (ok0) {
+                // heads with view-direction columns read base[viewdir] in S1 chunk 0 of the previous tile (just above); do
+                // not let fast warps overwrite it before everybody has read it
                 if (a.shading != T2N_SHADE_MLP_FEA_NOVIEW) producers_sync();
-                const int e0 = (blockIdx.x + j * gridDim.x) * kMmaM;
-                const int e = e0 + row;
-                const bool live = e < total;
-                Axis ax[3];
+                float* brow = base + row * kBaseStride;
                 if (live) {
-                    const int slot = __ldg(a.slots + e);
-                    const int r = slot / a.S;
-                    const float z = __ldg(a.z_vals + slot);
-                    const float* ray = a.rays + (size_t)r * 6;
                     RaySetup rs;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) { rs.o[q] = __ldg(ray + q); rs.d[q] = __ldg(ray + 3 + q); }
+                    rs.o[0] = ro0; rs.o[1] = ro1; rs.o[2] = ro2; rs.d[0] = rd0; rs.d[1] = rd1; rs.d[2] = rd2;
                     float p[3];
-                    sample_point(rs, z, p);
+                    sample_point(rs, gz, p);
                     const SampleGeom g = sample_geom(a.f, p);
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) ax[q] = make_axis(g.i0[q], g.fr[q], a.f.G[q]);
                     if (sub == 0) {
-                        float* brow = base + row * kBaseStride;
+                        int* gw = geo + row * 6;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { gw[q] = g.i0[q]; gw[3 + q] = __float_as_int(g.fr[q]); }
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
                             brow[a.app_dim + q] = rs.d[q];
@@ -425,51 +501,77 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                         brow[a.app_dim + 6] = 0.f;
                     }
                 } else if (sub == 0) {
-                    float* brow = base + row * kBaseStride;
                     for (int q = a.app_dim; q <= a.app_dim + 6; ++q) brow[q] = 0.f;
                 }
-                for (int c = 0; c < nk0; ++c, ++it) {
-                    const int comp0 = c * 32 + sub * 8;         // this thread's 8 product channels
-                    float4 prod[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) prod[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (live && comp0 < a.n_app_total) {
-                        const int i = comp0 >= a.aoff[2] ? 2 : (comp0 >= a.aoff[1] ? 1 : 0);
-                        const int ch0 = comp0 - a.aoff[i];
-                        const int a0 = (i == 2) ? 1 : 0, a1 = (i == 0) ? 1 : 2, v = 2 - i;
-                        const int C = a.ac[i], W = a.f.G[a0];
-                        const Axis &X = ax[a0], &Y = ax[a1], &Z = ax[v];
-                        const float nw = __fmul_rn(X.w0, Y.w0), ne = __fmul_rn(X.w1, Y.w0);
-                        const float sw = __fmul_rn(X.w0, Y.w1), se = __fmul_rn(X.w1, Y.w1);
-                        const float* Pp = a.ap[i] + ch0;
-                        const float* Lp = a.al[i] + ch0;
-                        const size_t o00 = ((size_t)Y.c0 * W + X.c0) * C, o01 = ((size_t)Y.c0 * W + X.c1) * C;
-                        const size_t o10 = ((size_t)Y.c1 * W + X.c0) * C, o11 = ((size_t)Y.c1 * W + X.c1) * C;
-                        float4 t00[2], t01[2], t10[2], t11[2], l0[2], l1[2];
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            t00[q] = ldg4(Pp + o00 + 4 * q); t01[q] = ldg4(Pp + o01 + 4 * q);
-                            t10[q] = ldg4(Pp + o10 + 4 * q); t11[q] = ldg4(Pp + o11 + 4 * q);
-                            l0[q] = ldg4(Lp + Z.c0 * C + 4 * q); l1[q] = ldg4(Lp + Z.c1 * C + 4 * q);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            float4 pv = f4_fma(se, t11[q], f4_fma(sw, t10[q], f4_fma(ne, t01[q], f4_scale(nw, t00[q]))));
-                            float4 lv = f4_fma(Z.w1, l1[q], f4_scale(Z.w0, l0[q]));
-                            prod[q] = f4_mul(pv, lv);
-                        }
-                    }
-                    stage_acquire(it, true);                    // loads above overlap the wait
-                    uint8_t* A_hi = sm + L.a[it & 1];
-                    uint8_t* A_lo = A_hi + kTileBytes;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) st_split4(A_hi, A_lo, sw128_off(row, sub * 2 + q), prod[q]);
-                    stage_publish(it);
-                }
+                __syncwarp();                   // geo[row] written by the row's sub 0, read by its four threads
+                unit_loads(0);
             }
-            // ================= S3(j-2): relu(D2 + b2) . W3 + b3 -> sigmoid =================
-            long long ts3 = clock64(); tS[0] += ts3 - ts2;
-            if (j - 2 >= 0 && j - 2 < n_tiles) {
+            tmark(kStepPro, ts0);
+            // ---- merged part: S1(j-1) chunks 1.. with the gather units of tile j in between
+            // (instantiated per validity combination so the steady-state loop carries no per-step tile checks)
+            auto merged = [&](auto kU, auto kS) {
+                for (int s = 0, uk = 0, sc = 1; s < n_merged; ++s) {
+                    if ((umask >> s) & 1u) {
+                        const int idx = uk++;
+                        if (!decltype(kU)::value) continue;
+                        ev(tr_j, tr_ci, (idx & 1) ? 3 : 0);
+                        float4 prod = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pf_have) {
+                            const float4 pv = f4_fma(w_se, pf3, f4_fma(w_sw, pf2, f4_fma(w_ne, pf1, f4_scale(w_nw, pf0))));
+                            const float4 lv = f4_fma(w_z1, pf5, f4_scale(w_z0, pf4));
+                            prod = f4_mul(pv, lv);
+                        }
+                        if (idx & 1) ev(tr_j, tr_ci, 1);
+                        if (idx + 1 < 2 * nk0) unit_loads(idx + 1);         // next unit's loads fly during the S1 chunks in between
+                        const int st = n0 & 1;
+                        if (!(idx & 1)) wait_done(st ? s0_last1 : s0_last0);   // stage free: the basis chunk two back has completed
+                        uint8_t* A_hi = sm + a_stage_off(st);
+                        st_split4(A_hi, A_hi + kTileBytes, sw128_off(row, (idx & 1) * 4 + sub), prod);
+                        if (idx & 1) {
+                            wait_done(it - 4);                              // a_full slot it & 3: the phase of chunk it-4 is over
+                            fence_async_smem();                             // generic-proxy writes -> async proxy
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_afull + (it & 3));
+                            ev(tr_j, tr_ci++, 2);
+                            if (st) s0_last1 = it; else s0_last0 = it;
+                            ++n0; ++it;
+                        }
+                        tmark(kStepU, ts0);
+                    } else {
+                        const int idx = sc++;
+                        if (!decltype(kS)::value) continue;
+                        ev(tr_j, tr_ci, 0);
+                        // frequency f, half h: (sin, cos)(x * 2^f) by angle doubling
+                        const int f = args.pe_chunks == 2 ? ((idx - 1) >> 1) : (idx - 1);
+                        const int h = args.pe_chunks == 2 ? ((idx - 1) & 1) : 0;
+                        if (h == 0 && f > 0) {
+    #pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float s2 = 2.f * sn[q];
+                                const float ns = s2 * cs[q];
+                                cs[q] = fmaf(-s2, sn[q], 1.f);
+                                sn[q] = ns;
+                            }
+                        }
+                        float cols[8];
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            cols[2 * q] = h ? sn[4 + q] : sn[q];
+                            cols[2 * q + 1] = h ? cs[4 + q] : cs[q];
+                        }
+                        wait_done(it - kTmemAStages);
+                        st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), 8 * eq, cols);
+                        publish_tmem();
+                        tmark(kStepS1, ts0);
+                    }
+                }
+            };
+            if (ok0 && ok1) merged(std::true_type{}, std::true_type{});
+            else if (ok0) merged(std::true_type{}, std::false_type{});
+            else if (ok1) merged(std::false_type{}, std::true_type{});
+            // ---- S3(j-2): relu(D2 + b2) . W3 + b3 -> sigmoid
+            if (ok2) {
                 const int e0 = (blockIdx.x + (j - 2) * gridDim.x) * kMmaM;
                 acc_wait(2, j - 2);
                 {
@@ -507,19 +609,18 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                     const int e = e0 + m;
                     if (e < total) {
                         const float* pm = part + m * 16 + c;
-                        const float s = (pm[0] + pm[4]) + (pm[8] + pm[12]) + b3s[c];
-                        a.app_rgb[(size_t)e * 3 + c] = 1.f / (1.f + expf(-s));
+                        const float sres = (pm[0] + pm[4]) + (pm[8] + pm[12]) + b3s[c];
+                        a.app_rgb[(size_t)e * 3 + c] = 1.f / (1.f + expf(-sres));
                     }
                 }
                 producers_sync();
             }
-            tS[3] += clock64() - ts3;
+            tmark(kStepS3, ts0);
         }
-        if (tr) {
+        if (TR && args.trace != nullptr && blockIdx.x == 0 && tid == 0) {
             args.trace[0] = clock64() - t0p;
-            for (int q = 0; q < 4; ++q) args.trace[1 + q] = tS[q];      // S0, S1, S2, S3 (incl. their waits)
-            for (int q = 0; q < 3; ++q) args.trace[5 + q] = wAcc[q];    // waits for D0, D1, D2
-            for (int q = 0; q < 3; ++q) args.trace[8 + q] = wSt[q];     // A-stage waits inside S2, S1, S0
+            for (int q = 0; q < 7; ++q) args.trace[1 + q] = tK[q];     // S2, S1, U, Pre, Ray, Pro, S3
+            args.trace[8] = w_acc; args.trace[9] = w_done;
             args.trace[11] = n_tiles;
         }
     }

@@ -86,6 +86,7 @@ inline bool build_mma_recipe(int shading, int app_dim, int fea_pe, int view_pe, 
     return true;
 }
 
+constexpr int kMaxProg = 80;
 constexpr int kNB = 4;  // B ring depth: a 32 KB weight chunk needs ~2 MMA-chunk times to arrive from L2
 struct MmaSmem {        // byte offsets from the 1024-aligned base
     int a[2];           // A stages: hi at +0, lo at +kTileBytes
@@ -95,6 +96,8 @@ struct MmaSmem {        // byte offsets from the 1024-aligned base
     int part;           // float [128][4][4] layer-3 partial sums
     int bars;           // uint64: b_full[4], b_free[4], a_free[2], a_full[2], acc[3]
     int tmem_slot;      // uint32
+    int prog;           // uint8 [kMaxProg] chunk program + int n_prog at +kMaxProg
+    int geo;            // int [128][6] per-sample texel index / fraction of the three axes
     int total;
 };
 __host__ __device__ inline MmaSmem mma_smem_layout() {
@@ -111,6 +114,8 @@ __host__ __device__ inline MmaSmem mma_smem_layout() {
     L.part = o; o += kMmaM * 4 * 4 * 4;
     L.bars = o; o += 16 * 8;
     L.tmem_slot = o; o += 16;
+    L.prog = o; o += kMaxProg + 16;
+    L.geo = o; o += kMmaM * 6 * 4;
     L.total = o + 1024;     // slack for the manual 1024-byte alignment of the base
     return L;
 }
@@ -145,7 +150,8 @@ struct AppMmaArgs {
     float* feat;            // [rows][32] appearance feature (basis output), zero padded
     long long act_rows;     // capacity of the three arrays in rows (multiple of 128)
     unsigned backoff_ns;    // nanosleep between polls of the producers' long mbarrier waits
-    long long* trace;       // debug: 32 cycle counters written by CTA 0 (NULL = off), see t2n_debug_trace_read
+    long long* trace;       // debug: cycle counters + timeline events written by CTA 0 (NULL = off), see t2n_debug_trace_read
+    int dbg;                // trace instantiation only: 1 = skip gather loads, 2 = skip MMAs, 4 = copy half of every weight chunk
 };
 
 }  // namespace t2n

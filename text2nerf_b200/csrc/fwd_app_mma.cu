@@ -3,9 +3,11 @@
 #include "appearance_mma.cuh"
 namespace t2n {
 int launch_app_forward_mma(const AppMmaArgs& a, int smem_bytes, int grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(app_forward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    // the cycle-counter instantiation is only launched by tools/trace_mma.py (T2N_MMA_TRACE)
+    auto kern = a.trace != nullptr ? app_forward_mma_kernel<true> : app_forward_mma_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return (int)e;
-    app_forward_mma_kernel<<<grid, kMmaThreads, smem_bytes, st>>>(a);
+    kern<<<grid, kMmaThreads, smem_bytes, st>>>(a);
     return (int)cudaGetLastError();
 }
 int launch_pack_mma(const AppArgs& a, const MmaRecipe& R, const float* w1, int K, float* out, cudaStream_t st) {

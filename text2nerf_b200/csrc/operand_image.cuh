@@ -12,6 +12,11 @@ __device__ __forceinline__ uint32_t tf32_hi(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// Cheap "hi" part for A-operand elements produced on the fly and multiplied with rna-split weights: the top 19 bits
+// (truncation).  x - hi is exact, has at most 13 significant bits and the tensor core reads its top 11, so the split is
+// good to 2^-21 of |x| (2^-23 with round-to-nearest -- but cvt.rna.tf32.f32 is a 4-instruction emulation on sm_100a).
+// Operand images (img_store8), where BOTH GEMM operands are split on the fly, keep the rounded split.
+__device__ __forceinline__ uint32_t tf32_trunc(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
 constexpr int kImgBlockRows = 16;
 constexpr int kImgGroupBytes = kImgBlockRows * 128;     // one [16 x 32 fp32] swizzled group of a block

@@ -13,7 +13,7 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
 }
 __device__ __forceinline__ void st_split4(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, float4 v) {
     uint4 h, l;
-    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    h.x = tf32_trunc(v.x); h.y = tf32_trunc(v.y); h.z = tf32_trunc(v.z); h.w = tf32_trunc(v.w);
     l.x = __float_as_uint(v.x - __uint_as_float(h.x));
     l.y = __float_as_uint(v.y - __uint_as_float(h.y));
     l.z = __float_as_uint(v.z - __uint_as_float(h.z));
@@ -61,7 +61,7 @@ __device__ __forceinline__ void st_split8_tmem(uint32_t a_stage_lane, int col, c
     uint32_t h[8], l[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        h[q] = tf32_hi(v[q]);
+        h[q] = tf32_trunc(v[q]);
         l[q] = __float_as_uint(v[q] - __uint_as_float(h[q]));
     }
     tmem_st8(a_stage_lane + col, h);
