@@ -307,6 +307,23 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                 done_known = p;
             }
         };
+        // Split-phase form for the TS chunks: the try_wait is a long-scoreboard operation (~100+ cycles even when the phase is
+        // long over), so it is issued before the chunk's columns are computed and its predicate is consumed after.
+        auto poll_done = [&](int p) -> uint32_t {
+            uint32_t ok = 1;
+            if (p > done_known)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(bar_done + (p & 3))), "r"((uint32_t)(p >> 2) & 1u) : "memory");
+            return ok;
+        };
+        auto finish_done = [&](int p, uint32_t ok) {
+            if (!ok) wait_done(p);
+            else if (p > done_known) done_known = p;
+        };
+        auto split8 = [&](const float (&v)[8], uint32_t (&h)[8], uint32_t (&l)[8]) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { h[q] = tf32_trunc(v[q]); l[q] = __float_as_uint(v[q] - __uint_as_float(h[q])); }
+        };
         int tr_j = 0, tr_ci = 0;
         auto publish_tmem = [&]() {     // tcgen05.st writes complete, then one arrival per warp
             ev(tr_j, tr_ci, 1);
@@ -336,7 +353,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
         // gather state of tile j
         bool live = false, pf_have = false;
         int slot = 0;
-        float gz = 0.f, ro0 = 0.f, ro1 = 0.f, ro2 = 0.f, rd0 = 0.f, rd1 = 0.f, rd2 = 0.f;
+        float2 rq = make_float2(0.f, 0.f);                 // this thread's quarter of the sample's (ray, z) prefetch
         float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f), pf1 = pf0, pf2 = pf0, pf3 = pf0, pf4 = pf0, pf5 = pf0;
         float w_nw = 0.f, w_ne = 0.f, w_sw = 0.f, w_se = 0.f, w_z0 = 0.f, w_z1 = 0.f;
         const float* pl_ptr = a.ap[0];      // footprint of the current plane: texel (y0, x0) minus the plane's channel offset
@@ -395,6 +412,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             ev(tr_j, tr_ci, 0);
             if (c == 0) acc_wait(1, j - 2);
             const int e_row = (blockIdx.x + (j - 2) * gridDim.x) * kMmaM + erow;
+            const uint32_t rdy = poll_done(it - kTmemAStages);
             uint32_t v[8];
             const int col0 = c * 32 + eq * 8;
             tmem_ld8(tmem + tmem_lane + kColD1 + col0, v);
@@ -403,8 +421,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             for (int q = 0; q < 8; ++q) h[q] = fmaxf(__uint_as_float(v[q]) + b1s[col0 + q], 0.f);
             if (args.h1_img != nullptr && e_row < args.act_rows)        // operand image for the backward (all 128 rows)
                 img_store8(args.h1_img + (size_t)(e_row >> 7) * img_tile_bytes(4), 4, erow, c, eq, h);
-            wait_done(it - kTmemAStages);
-            st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), eq * 8, h);
+            uint32_t hh[8], ll[8];
+            split8(h, hh, ll);
+            finish_done(it - kTmemAStages, rdy);
+            const uint32_t ta = tmem + tmem_lane + kColA + 64 * (it % kTmemAStages) + eq * 8;
+            tmem_st8(ta, hh);
+            tmem_st8(ta + 32, ll);
             publish_tmem();
         };
 
@@ -424,12 +446,15 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             if (ok2) for (int c = 0; c < early; ++c) s2_chunk(j, c);
             tmark(kStepS2, ts0);
             // ---- Ray(j): z and the ray of the slot
+            // (the four threads of a sample share the work: sub 0..2 fetch one float2 of the ray each, sub 3 fetches z; Pro
+            // exchanges them with shuffles -- two prefetch registers per thread instead of seven)
             if (ok0 && live) {
-                const int r = slot / a.S;
-                gz = __ldg(a.z_vals + slot);
-                const float2* rp = reinterpret_cast<const float2*>(a.rays + (size_t)r * 6);
-                const float2 u0 = __ldg(rp), u1 = __ldg(rp + 1), u2 = __ldg(rp + 2);
-                ro0 = u0.x; ro1 = u0.y; ro2 = u1.x; rd0 = u1.y; rd1 = u2.x; rd2 = u2.y;
+                if (sub == 3) {
+                    rq.x = __ldg(a.z_vals + slot);
+                } else {
+                    const int r = slot / a.S;
+                    rq = __ldg(reinterpret_cast<const float2*>(a.rays + (size_t)r * 6) + sub);
+                }
             }
             tmark(kStepRay, ts0);
             if (ok2) for (int c = early; c < nk2; ++c) s2_chunk(j, c);
@@ -483,9 +508,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                 // not let fast warps overwrite it before everybody has read it
                 if (a.shading != T2N_SHADE_MLP_FEA_NOVIEW) producers_sync();
                 float* brow = base + row * kBaseStride;
+                const int q0 = lane & ~3;
+                const float u0x = __shfl_sync(T2N_FULL, rq.x, q0), u0y = __shfl_sync(T2N_FULL, rq.y, q0);
+                const float u1x = __shfl_sync(T2N_FULL, rq.x, q0 + 1), u1y = __shfl_sync(T2N_FULL, rq.y, q0 + 1);
+                const float u2x = __shfl_sync(T2N_FULL, rq.x, q0 + 2), u2y = __shfl_sync(T2N_FULL, rq.y, q0 + 2);
+                const float gz = __shfl_sync(T2N_FULL, rq.x, q0 + 3);
                 if (live) {
                     RaySetup rs;
-                    rs.o[0] = ro0; rs.o[1] = ro1; rs.o[2] = ro2; rs.d[0] = rd0; rs.d[1] = rd1; rs.d[2] = rd2;
+                    rs.o[0] = u0x; rs.o[1] = u0y; rs.o[2] = u1x; rs.d[0] = u1y; rs.d[1] = u2x; rs.d[2] = u2y;
                     float p[3];
                     sample_point(rs, gz, p);
                     const SampleGeom g = sample_geom(a.f, p);
@@ -542,6 +572,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                         const int idx = sc++;
                         if (!decltype(kS)::value) continue;
                         ev(tr_j, tr_ci, 0);
+                        const uint32_t rdy = poll_done(it - kTmemAStages);
                         // frequency f, half h: (sin, cos)(x * 2^f) by angle doubling
                         const int f = args.pe_chunks == 2 ? ((idx - 1) >> 1) : (idx - 1);
                         const int h = args.pe_chunks == 2 ? ((idx - 1) & 1) : 0;
@@ -560,8 +591,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                             cols[2 * q] = h ? sn[4 + q] : sn[q];
                             cols[2 * q + 1] = h ? cs[4 + q] : cs[q];
                         }
-                        wait_done(it - kTmemAStages);
-                        st_split8_tmem(tmem + tmem_lane + kColA + 64 * (it % kTmemAStages), 8 * eq, cols);
+                        uint32_t hh[8], ll[8];
+                        split8(cols, hh, ll);
+                        finish_done(it - kTmemAStages, rdy);
+                        const uint32_t ta = tmem + tmem_lane + kColA + 64 * (it % kTmemAStages) + 8 * eq;
+                        tmem_st8(ta, hh);
+                        tmem_st8(ta + 32, ll);
                         publish_tmem();
                         tmark(kStepS1, ts0);
                     }

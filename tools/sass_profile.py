@@ -12,6 +12,7 @@ import sys
 
 sass_csv, gi, fn, srcfile = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 50
+INNER = len(sys.argv) > 6 and sys.argv[6] == 'inner'   # attribute to the innermost line of the file instead of the outermost
 rows = list(csv.reader(open(sass_csv)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
@@ -33,7 +34,7 @@ for l in open(gi).read().splitlines():
         else:
             pending = list(allm)
         key = None
-        for ff, nn in pending:
+        for ff, nn in (reversed(pending) if INNER else pending):     # pending[0] is the innermost location
             if ff.endswith(base):
                 key = int(nn)
         cur = key if key is not None else (pending[0][0].split('/')[-1], int(pending[0][1]))
