@@ -298,10 +298,19 @@ def main():
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+    # `ncu --set full` capture of this same workload (bench.py never runs under the profiler)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if dom in tj:
+            traffic, traffic_src = float(tj[dom]["dram_bytes_per_launch"]), tj[dom]["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     achieved = kbytes[dom] / (kavg[dom] * 1e-3) / 1e9
     total_bytes = n_rays * (40 + 8 * S) + n_valid * 1152 + n_app * 3456
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel_ms": kavg, "kernel_algorithmic_bytes": kbytes,
                 "path_algorithmic_GBps": total_bytes / (ms_fwd / args.steps * 1e-3) / 1e9,

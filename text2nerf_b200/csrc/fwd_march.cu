@@ -3,11 +3,15 @@
 namespace t2n {
 template <int NQ>
 static int go(const MarchArgs& a, int line_bytes, int grid, cudaStream_t st) {
-    if (line_bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(march_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, line_bytes);
-        if (e != cudaSuccess) return (int)e;
+    if (a.lines_in_smem) {
+        if (line_bytes > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(march_kernel<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, line_bytes);
+            if (e != cudaSuccess) return (int)e;
+        }
+        march_kernel<NQ, true><<<grid, 256, line_bytes, st>>>(a);
+    } else {
+        march_kernel<NQ, false><<<grid, 256, 0, st>>>(a);
     }
-    march_kernel<NQ><<<grid, 256, line_bytes, st>>>(a);
     return (int)cudaGetLastError();
 }
 int launch_march(const MarchArgs& a, int nq, int line_bytes, int grid, cudaStream_t st) {

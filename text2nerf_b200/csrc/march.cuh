@@ -60,8 +60,10 @@ __device__ __forceinline__ SampleGeom sample_geom(const FieldDev& f, const float
     return g;
 }
 
-// Partial density feature of one sample for this lane's channel quads.  NQ = ceil(Cmax/16).
-template <int NQ>
+// Partial density feature of one sample for this lane's channel quads.  NQ = ceil(Cmax/16).  LS: the line factors live
+// in shared memory (explicit LDS instead of generic loads).  Texel addresses are one 64-bit base per plane plus 32-bit
+// +x / +y steps (0 when the neighbour is clamped onto the same texel).
+template <int NQ, bool LS>
 __device__ __forceinline__ float sigma_partial(const MarchArgs& a, const float* const* lines,
                                                const Axis ax[3], int c4) {
     float part = 0.f;
@@ -77,18 +79,18 @@ __device__ __forceinline__ float sigma_partial(const MarchArgs& a, const float* 
         const Axis& Z = ax[v];
         const float nw = __fmul_rn(X.w0, Y.w0), ne = __fmul_rn(X.w1, Y.w0);
         const float sw = __fmul_rn(X.w0, Y.w1), se = __fmul_rn(X.w1, Y.w1);
-        const float* P = a.sp[i];
-        const size_t o00 = ((size_t)Y.c0 * W + X.c0) * C, o01 = ((size_t)Y.c0 * W + X.c1) * C;
-        const size_t o10 = ((size_t)Y.c1 * W + X.c0) * C, o11 = ((size_t)Y.c1 * W + X.c1) * C;
-        const float* L = lines[i];
+        const float* P = a.sp[i] + ((size_t)Y.c0 * W + X.c0) * C + c4 * 4;
+        const int dx = (X.c1 - X.c0) * C, dy = (Y.c1 - Y.c0) * W * C;
+        const float* L0 = lines[i] + Z.c0 * C + c4 * 4;
+        const int dz = (Z.c1 - Z.c0) * C;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const int ch = (q * 4 + c4) * 4;
-            if (ch < C) {
-                float4 t00 = ldg4(P + o00 + ch), t01 = ldg4(P + o01 + ch);
-                float4 t10 = ldg4(P + o10 + ch), t11 = ldg4(P + o11 + ch);
-                float4 l0 = a.lines_in_smem ? lds4(L + Z.c0 * C + ch) : ldg4(L + Z.c0 * C + ch);
-                float4 l1 = a.lines_in_smem ? lds4(L + Z.c1 * C + ch) : ldg4(L + Z.c1 * C + ch);
+            const int ch = q * 16;
+            if (ch + c4 * 4 < C) {
+                float4 t00 = ldg4(P + ch), t01 = ldg4(P + dx + ch);
+                float4 t10 = ldg4(P + dy + ch), t11 = ldg4(P + dy + dx + ch);
+                float4 l0 = LS ? lds4(L0 + ch) : ldg4(L0 + ch);
+                float4 l1 = LS ? lds4(L0 + dz + ch) : ldg4(L0 + dz + ch);
                 float4 pv = f4_fma(se, t11, f4_fma(sw, t10, f4_fma(ne, t01, f4_scale(nw, t00))));
                 float4 lv = f4_fma(Z.w1, l1, f4_scale(Z.w0, l0));
                 part += f4_dot(pv, lv);
@@ -98,7 +100,7 @@ __device__ __forceinline__ float sigma_partial(const MarchArgs& a, const float* 
     return part;
 }
 
-template <int NQ>
+template <int NQ, bool LS>
 __global__ void __launch_bounds__(256) march_kernel(const __grid_constant__ MarchArgs a) {
     extern __shared__ __align__(128) float smem_lines[];
     __shared__ __align__(8) uint64_t bar;
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) march_kernel(const __grid_constant__ Marc
     const int warps_per_cta = blockDim.x >> 5;
 
     const float* lines[3] = {a.sl[0], a.sl[1], a.sl[2]};
-    if (a.lines_in_smem) {
+    if (LS) {
         // stage the three line factors with TMA bulk copies (UBLKCP) onto one mbarrier
         uint32_t bytes[3];
         float* dst[3];
@@ -162,6 +164,10 @@ __global__ void __launch_bounds__(256) march_kernel(const __grid_constant__ Marc
             if (!train) valid = valid && (p[2] > f.z_min);
             const SampleGeom g = sample_geom(f, p);
             const unsigned vmask = __ballot_sync(T2N_FULL, valid);
+            // bilinear footprint per axis of this lane's own sample, handed to the sample's four gather lanes below
+            Axis own[3];
+#pragma unroll
+            for (int ax_i = 0; ax_i < 3; ++ax_i) own[ax_i] = make_axis(g.i0[ax_i], g.fr[ax_i], f.G[ax_i]);
 
             // ---- gather phase
             float feat = -CUDART_INF_F;
@@ -174,12 +180,13 @@ __global__ void __launch_bounds__(256) march_kernel(const __grid_constant__ Marc
                     Axis ax[3];
 #pragma unroll
                     for (int ax_i = 0; ax_i < 3; ++ax_i) {
-                        int i0 = __shfl_sync(T2N_FULL, g.i0[ax_i], src);
-                        float fr = __shfl_sync(T2N_FULL, g.fr[ax_i], src);
-                        ax[ax_i] = make_axis(i0, fr, f.G[ax_i]);
+                        ax[ax_i].c0 = __shfl_sync(T2N_FULL, own[ax_i].c0, src);
+                        ax[ax_i].c1 = __shfl_sync(T2N_FULL, own[ax_i].c1, src);
+                        ax[ax_i].w0 = __shfl_sync(T2N_FULL, own[ax_i].w0, src);
+                        ax[ax_i].w1 = __shfl_sync(T2N_FULL, own[ax_i].w1, src);
                     }
                     float part = 0.f;
-                    if ((sub >> grp) & 1u) part = sigma_partial<NQ>(a, lines, ax, c4);
+                    if ((sub >> grp) & 1u) part = sigma_partial<NQ, LS>(a, lines, ax, c4);
                     part += __shfl_xor_sync(T2N_FULL, part, 1);
                     part += __shfl_xor_sync(T2N_FULL, part, 2);
                     // sample 8s+g lives in lanes 4g..4g+3; hand it to lane 8s+g
