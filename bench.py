@@ -330,32 +330,42 @@ def main():
                             (2 + 4 * torch.rand(TRAIN_BATCH, generator=g)).to(dev)))
         torch.manual_seed(7 + rank)
 
-        def train_step():
+        def train_step():           # fused data loss (TensorBase.data_loss): forward, loss kernel, backward kernels
+            for rays_b, rgb_gt, depth_gt in batches:
+                flat.zero_()
+                model.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S).backward()
+                t2n_dist.allreduce_flat_grads(model, world)
+
+        def train_step_composed():  # the same step written as the reference writes it: tensor ops on the four outputs
             for rays_b, rgb_gt, depth_gt in batches:
                 flat.zero_()
                 out = model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S)
-                loss = orc.training_loss(*out, rgb_gt, depth_gt)
-                loss.backward()
+                orc.training_loss(*out, rgb_gt, depth_gt).backward()
                 t2n_dist.allreduce_flat_grads(model, world)
 
         for _ in range(max(args.warmup, 3)):
             train_step()
         ms_tr = timed(train_step, args.steps)
+        for _ in range(2):
+            train_step_composed()
+        ms_tr_c = timed(train_step_composed, args.steps)
         rays_done = world * TRAIN_BATCH * TRAIN_BATCHES_PER_STEP * args.steps
         fwd_bwd = {"value": rays_done / (ms_tr * 1e-3) / 1e6, "unit": "Mrays/s", "batch_rays_per_gpu": TRAIN_BATCH,
                    "ms_per_batch": ms_tr / (args.steps * TRAIN_BATCHES_PER_STEP),
-                   "loss": "rgb MSE + 0.005 depth MSE + 1e3 transmittance (text2nerf_main.py:563-575), no optimiser step",
+                   "loss": "rgb MSE + 0.005 depth MSE + 1e3 transmittance (text2nerf_main.py:563-575) through the fused "
+                           "TensorBase.data_loss, no optimiser step",
+                   "composed_autograd_value": rays_done / (ms_tr_c * 1e-3) / 1e6,
                    "collective": "1 NCCL all-reduce of the flat fp32 grad buffer per batch" if world > 1 else "none (1 GPU)"}
         lib.t2n_profile_enable(1)
         rays_b, rgb_gt, depth_gt = batches[0]
         flat.zero_()
-        out = model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S)
+        loss = model.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S)
         fk = dict(nat.profile_read())
-        orc.training_loss(*out, rgb_gt, depth_gt).backward()
+        loss.backward()
         bk = dict(nat.profile_read())
         lib.t2n_profile_enable(0)
         fwd_bwd["kernel_ms"] = {**fk, **bk}
-        launches_train = 15 * TRAIN_BATCHES_PER_STEP * args.steps    # march, pack, app, finalize | pack_bwd, bwd-data, 4 wgrad, (pack_w1, ffma fallback, unpack: early exit), ray_backward
+        launches_train = 16 * TRAIN_BATCHES_PER_STEP * args.steps    # march, pack, app, finalize, data_loss | pack_bwd, bwd-data, 4 wgrad, (pack_w1, ffma fallback, unpack: early exit), ray_backward
         model.enable_flat_grads(False)
 
     # ---------------- CPU baseline (rank 0, N=1 only)

@@ -222,6 +222,34 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
                         const float* g_rgb_map, const float* g_depth_map, const float* g_weight,
                         const T2NGrads* grads, t2n_stream_t stream);
 
+/* Compact gradient of the transmittance loss with respect to weight (see t2n_data_loss): g_weight[r][k] =
+ * coef[r] * [(z_vals[r][k] - depth_gt[r]) + delta < 0].  All device pointers. */
+typedef struct T2NTransGrad {
+    const float* coef;      /* [R] */
+    const float* depth_gt;  /* [R] */
+    float delta;
+} T2NTransGrad;
+
+/* t2n_render_backward with the weight gradient given in compact form (g_weight must then be NULL); trans_grad may be
+ * NULL, which makes this identical to t2n_render_backward. */
+int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                           const T2NBatch* batch, const T2NOutputs* out, const T2NScratch* scratch,
+                           const float* g_rgb_map, const float* g_depth_map, const float* g_weight,
+                           const T2NTransGrad* trans_grad, const T2NGrads* grads, t2n_stream_t stream);
+
+/* Fused data loss of the Text2NeRF training step, text2nerf_main.py:559-575 with utils.TransMittanceLoss_mask
+ * (utils.py:67-80), from the forward's outputs:
+ *   loss = mean((rgb_map - rgb_gt)^2) + w_depth * mean((nan_to_0(depth_map) - depth_gt)^2)
+ *        + w_trans * mean_r( mean_k(weight * [(z_vals - depth_gt) + delta < 0])^2 )
+ * Writes per-ray unscaled terms ray_terms [R][3] = (sum_c rgb diff^2, depth diff^2, mean_w^2) -- the caller reduces
+ * them: loss = inv_scale * (sum(t0)/3 + w_depth*sum(t1) + w_trans*sum(t2)) -- and the loss gradients g_rgb_map [R][3],
+ * g_depth_map [R] and the compact weight gradient gw_coef [R] (T2NTransGrad::coef); g_weight_dense [R][S] is optional
+ * (NULL = do not materialise).  inv_scale = 1 / (number of rays the means run over). */
+int t2n_data_loss(const T2NOutputs* out, int R, int S, const float* rgb_gt, const float* depth_gt,
+                  float w_depth, float w_trans, float delta, float inv_scale,
+                  float* ray_terms, float* g_rgb_map, float* g_depth_map, float* gw_coef, float* g_weight_dense,
+                  t2n_stream_t stream);
+
 /* Camera rays of one view: get_ray_directions (+ optional per-pixel normalisation as
  * dataLoader/scene_gen.py:45 applies) followed by get_rays (dataLoader/ray_utils.py:24-42,
  * 66-87).  c2w is a HOST pointer to 12 floats (row-major 3x4).  rays [H*W][6]. */

@@ -93,3 +93,17 @@ def scaled_err(a, b):
 def cosine(a, b):
     a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+def fused_loss_with_jitter(model, rays, jitter, white_bg_effective, n_samples, rgb_gt, depth_gt,
+                           w_depth=0.005, w_trans=1e3, delta=0.1, n_rays_total=None):
+    """TensorBase.data_loss with an explicit per-ray jitter (bypasses the CPU RNG draws)."""
+    from text2nerf_b200.tensorBase import _FusedLossFn
+    S = n_samples if n_samples > 0 else model.nSamples
+    dev = rays.device
+    jit = jitter.reshape(-1).to(dev).contiguous()
+    R = rays.shape[0]
+    return _FusedLossFn.apply(model, rays.contiguous(), jit, S, bool(white_bg_effective),
+                              rgb_gt.to(dev).float().reshape(R, 3).contiguous(), depth_gt.to(dev).float().reshape(R).contiguous(),
+                              float(w_depth), float(w_trans), float(delta), 1.0 / float(n_rays_total or R),
+                              torch.is_grad_enabled(), *model._flat_params())

@@ -72,6 +72,10 @@ class T2NOutputs(C.Structure):
                 ("weight", C.c_void_p)]
 
 
+class T2NTransGrad(C.Structure):
+    _fields_ = [("coef", C.c_void_p), ("depth_gt", C.c_void_p), ("delta", C.c_float)]
+
+
 class T2NScratch(C.Structure):
     _fields_ = [("sigma_feat", C.c_void_p), ("trans", C.c_void_p), ("acc", C.c_void_p),
                 ("dsum", C.c_void_p), ("ray_start", C.c_void_p), ("ray_count", C.c_void_p),
@@ -98,6 +102,13 @@ SYMBOLS = {
     "t2n_render_backward": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
                                       C.POINTER(T2NBatch), C.POINTER(T2NOutputs), C.POINTER(T2NScratch),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(T2NGrads), C.c_void_p]),
+    "t2n_render_backward_tg": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
+                                         C.POINTER(T2NBatch), C.POINTER(T2NOutputs), C.POINTER(T2NScratch),
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(T2NTransGrad),
+                                         C.POINTER(T2NGrads), C.c_void_p]),
+    "t2n_data_loss": (C.c_int, [C.POINTER(T2NOutputs), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "t2n_get_rays": (C.c_int, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "t2n_rotate_rays": (C.c_int, [C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -142,7 +153,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
 
 
 KERNEL_NAMES = {0: "march", 1: "pack_w1", 2: "appearance", 3: "finalize", 4: "app_backward_ffma",
-                5: "unpack_w1_grad", 6: "ray_backward", 7: "pack_bwd", 8: "app_backward_mma", 9: "wgrad"}
+                5: "unpack_w1_grad", 6: "ray_backward", 7: "pack_bwd", 8: "app_backward_mma", 9: "wgrad", 10: "data_loss"}
 
 
 def profile_read():

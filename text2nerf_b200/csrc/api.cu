@@ -338,8 +338,38 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
                         const T2NBatch* batch, const T2NOutputs* out, const T2NScratch* scratch,
                         const float* g_rgb_map, const float* g_depth_map, const float* g_weight,
                         const T2NGrads* grads, t2n_stream_t stream) {
+    return t2n_render_backward_tg(field, params, mask, batch, out, scratch, g_rgb_map, g_depth_map, g_weight, nullptr, grads,
+                                  stream);
+}
+
+int t2n_data_loss(const T2NOutputs* out, int R, int S, const float* rgb_gt, const float* depth_gt,
+                  float w_depth, float w_trans, float delta, float inv_scale,
+                  float* ray_terms, float* g_rgb_map, float* g_depth_map, float* gw_coef, float* g_weight_dense,
+                  t2n_stream_t stream) {
+    if (!out || !out->rgb_map || !out->depth_map || !out->z_vals || !out->weight || !rgb_gt || !depth_gt || !ray_terms ||
+        !g_rgb_map || !g_depth_map || !gw_coef || R < 0 || S <= 0)
+        return T2N_E_BADARG;
+    DeviceInfo& dev = device_info();
+    if (!dev.ok || dev.cc_major != 10) return T2N_E_DEVICE;
+    if (R == 0) return 0;
+    DataLossArgs a;
+    a.rgb_map = out->rgb_map; a.depth_map = out->depth_map; a.z_vals = out->z_vals; a.weight = out->weight;
+    a.rgb_gt = rgb_gt; a.depth_gt = depth_gt; a.R = R; a.S = S;
+    a.w_depth = w_depth; a.w_trans = w_trans; a.delta = delta; a.inv_scale = inv_scale;
+    a.ray_terms = ray_terms; a.g_rgb = g_rgb_map; a.g_depth = g_depth_map; a.gw_coef = gw_coef; a.g_weight = g_weight_dense;
+    g_prof.start(10, reinterpret_cast<cudaStream_t>(stream));
+    const int rc = launch_data_loss(a, reinterpret_cast<cudaStream_t>(stream));
+    g_prof.stop(reinterpret_cast<cudaStream_t>(stream));
+    return rc;
+}
+
+int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                           const T2NBatch* batch, const T2NOutputs* out, const T2NScratch* scratch,
+                           const float* g_rgb_map, const float* g_depth_map, const float* g_weight,
+                           const T2NTransGrad* trans_grad, const T2NGrads* grads, t2n_stream_t stream) {
     int rc = check_field(field, params);
     if (rc) return rc;
+    if (trans_grad && (g_weight || !trans_grad->coef || !trans_grad->depth_gt)) return T2N_E_BADARG;
     if (!batch || !out || !scratch || !grads || !g_rgb_map || !g_depth_map) return T2N_E_BADARG;
     if (!scratch->sigma_feat || !scratch->trans || !scratch->ray_flags) return T2N_E_BADARG;
     DeviceInfo& dev = device_info();
@@ -503,6 +533,7 @@ int t2n_render_backward(const T2NField* field, const T2NParams* params, const T2
         a.z_vals = out->z_vals; a.weight = out->weight; a.sigma_feat = scratch->sigma_feat; a.trans = scratch->trans;
         a.ray_start = scratch->ray_start; a.ray_count = scratch->ray_count; a.ray_flags = scratch->ray_flags;
         a.app_rgb = scratch->app_rgb; a.g_rgb = g_rgb_map; a.g_depth = g_depth_map; a.g_weight = g_weight;
+        if (trans_grad) { a.gw_coef = trans_grad->coef; a.depth_gt = trans_grad->depth_gt; a.delta = trans_grad->delta; }
         int ctas_per_sm = line_bytes > 0 ? (int)((220 * 1024) / (line_bytes + 1024)) : 4;
         ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
         int grid = dev.sm_count * ctas_per_sm;

@@ -41,6 +41,11 @@ struct RayBwdArgs {
     const float* g_rgb;
     const float* g_depth;
     const float* g_weight;      // nullable
+    // compact gradient of the transmittance loss (loss.cuh): g_weight[r][k] = gw_coef[r] * [(z - depth_gt[r]) + delta < 0];
+    // used when g_weight is NULL and gw_coef is not
+    const float* gw_coef;
+    const float* depth_gt;
+    float delta;
 };
 
 __device__ __forceinline__ void red_add_smem(float* p, float v) {
@@ -166,6 +171,8 @@ __global__ void __launch_bounds__(256) ray_backward_kernel(const __grid_constant
 #pragma unroll
         for (int c = 0; c < 3; ++c) G[c] = ((flags >> c) & 1) ? __ldg(a.g_rgb + r * 3 + c) : 0.f;
         const float gd = __ldg(a.g_depth + r);
+        const float gw_c = a.gw_coef ? __ldg(a.gw_coef + r) : 0.f;
+        const float gt_depth = a.gw_coef ? __ldg(a.depth_gt + r) : 0.f;
         // d/dacc: rgb_map += (1-acc) when white; depth_map += (1-acc)*d_z
         const float g_acc = (a.white_bg ? -(G[0] + G[1] + G[2]) : 0.f) - gd * rs.d[2];
         const int start = a.ray_start[r];
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(256) ray_backward_kernel(const __grid_constant
                 T = __ldg(a.trans + row + k);
                 sf = __ldg(a.sigma_feat + row + k);
                 if (a.g_weight) gwt = __ldg(a.g_weight + row + k);
+                else if (a.gw_coef) gwt = (__fadd_rn(__fsub_rn(z, gt_depth), a.delta) < 0.f) ? gw_c : 0.f;
             }
             const bool valid = in && (sf > -CUDART_INF_F);
             const float sigma = valid ? density_act(f, sf) : 0.f;

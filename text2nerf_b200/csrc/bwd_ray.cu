@@ -1,4 +1,4 @@
-// ray sweep backward launcher
+// ray sweep backward + fused data loss launchers
 #include "launch.h"
 namespace t2n {
 template <int NQ>
@@ -17,5 +17,10 @@ int launch_ray_backward(const RayBwdArgs& a, int nq, int smem, int grid, cudaStr
         case 3: return go<3>(a, smem, grid, st);
         default: return go<4>(a, smem, grid, st);
     }
+}
+int launch_data_loss(const DataLossArgs& a, cudaStream_t st) {
+    const int grid = (int)(((long long)a.R * 32 + 255) / 256);
+    data_loss_kernel<<<grid, 256, 0, st>>>(a);
+    return (int)cudaGetLastError();
 }
 }  // namespace t2n

@@ -6,6 +6,7 @@
 #include "backward.cuh"
 #include "appearance_mma_defs.cuh"
 #include "bwd_mma_defs.cuh"
+#include "loss.cuh"
 
 
 namespace t2n {
@@ -21,5 +22,6 @@ int launch_unpack_w1_grad(const float* gw1p, const int32_t* perm, int C, int K, 
 int launch_pack_bwd(const BwdPackArgs& a, cudaStream_t st);
 int launch_app_backward_mma(const BwdMmaArgs& a, int smem_bytes, int grid, cudaStream_t st);
 int launch_wgrad(WgradArgs& a, int max_smem, int grid, cudaStream_t st);
+int launch_data_loss(const DataLossArgs& a, cudaStream_t st);
 int launch_make_image(const float* rows, int n_rows, int ng, uint8_t* img, cudaStream_t st);
 }  // namespace t2n

@@ -224,106 +224,175 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _render_forward(model, rays, jitter, n_samples, is_train, white_bg, need_bwd, params):
+    """t2n_render_forward on one ray batch.  Returns (rgb_map, depth_map, z_vals, weight), the scratch dict the
+    backward needs, and the channels-last parameter tensors the kernels read."""
+    lib = nat.load()
+    dev = rays.device
+    R, S = rays.shape[0], n_samples
+    if need_bwd:
+        model._poll_listed_count()
+    p_cl = model._native_param_tensors(params)
+    field = model._native_field()
+    pstruct = model._native_params(p_cl)
+    f32 = dict(device=dev, dtype=torch.float32)
+    i32 = dict(device=dev, dtype=torch.int32)
+    rgb_map = torch.empty((R, 3), **f32)
+    depth_map = torch.empty((R,), **f32)
+    z_vals = torch.empty((R, S), **f32)
+    weight = torch.empty((R, S), **f32)
+    sc = dict(
+        sigma_feat=torch.empty((R, S), **f32) if need_bwd else None,
+        trans=torch.empty((R, S), **f32) if need_bwd else None,
+        acc=torch.empty((R,), **f32), dsum=torch.empty((R,), **f32),
+        ray_start=torch.empty((R,), **i32), ray_count=torch.empty((R,), **i32),
+        slots=torch.empty((R * S,), **i32), app_rgb=torch.empty((R * S, 3), **f32),
+        counters=torch.empty((8,), **i32),
+        w1_packed=model._w1_packed_buffer(dev),
+        ray_flags=torch.empty((R,), **i32),
+        w1_grad_packed=None,
+        mma_pack=model._mma_pack_buffer(dev, field), act_h1_img=None, act_h2_img=None, act_feat=None,
+        act_rows=0, bwd_pack=None, bwd_img=None)
+    if need_bwd and sc["mma_pack"] is not None and int(field.feature_c) == 128:
+        # training state of the tensor-core backward: decoder activations as operand images + features,
+        # sized from the running estimate of listed samples (a batch that overflows it takes the FFMA path)
+        rows = model._act_capacity(R, S)
+        sc["act_rows"] = rows
+        sc["act_h1_img"] = torch.empty((rows * 1024,), device=dev, dtype=torch.uint8)
+        sc["act_h2_img"] = torch.empty((rows * 1024,), device=dev, dtype=torch.uint8)
+        sc["act_feat"] = torch.empty((rows, 32), **f32)
+    mask = model.alphaMask.native() if model.alphaMask is not None else None
+    batch = nat.T2NBatch(_ptr(rays), _ptr(jitter), R, S, int(is_train), int(white_bg))
+    outs = nat.T2NOutputs(_ptr(rgb_map), _ptr(depth_map), _ptr(z_vals), _ptr(weight))
+    scratch = nat.T2NScratch(*[sc[k] if k == "act_rows" else _ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.t2n_render_forward(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
+                                    C.byref(batch), C.byref(outs), C.byref(scratch), stream)
+    nat.check(rc, "t2n_render_forward")
+    model._last_counters = sc["counters"]
+    if need_bwd:
+        model._post_listed_count(sc["counters"])
+    model._last_scratch = sc if os.environ.get("T2N_KEEP_SCRATCH") else None
+    return (rgb_map, depth_map, z_vals, weight), sc, p_cl
+
+
+def _render_backward(model, sc, rays, jitter, n_samples, is_train, white_bg, z_vals, weight, rgb_map, p_cl,
+                     g_rgb, g_depth, g_w, trans_grad=None):
+    """t2n_render_backward(_tg): gradients of a scalar loss into the model's gradient buffers.  trans_grad =
+    (gw_coef [R], depth_gt [R], delta): the weight gradient in compact form (g_w must be None)."""
+    lib = nat.load()
+    R, S = rays.shape[0], n_samples
+    dev = rays.device
+    field = model._native_field()
+    pstruct = model._native_params(p_cl)
+    grads = model._grad_buffers(p_cl)
+    gstruct = model._native_grads(grads)
+    if model._is_mlp:
+        sc["w1_grad_packed"] = torch.empty_like(sc["w1_packed"])
+    if sc["act_rows"]:
+        npack = int(lib.t2n_bwd_pack_floats(C.byref(field)))
+        row_bytes = int(lib.t2n_bwd_image_row_bytes(C.byref(field)))
+        if npack and row_bytes:
+            sc["bwd_pack"] = torch.empty((npack,), device=dev, dtype=torch.float32)
+            sc["bwd_img"] = torch.empty((sc["act_rows"] * row_bytes,), device=dev, dtype=torch.uint8)
+    mask = model.alphaMask.native() if model.alphaMask is not None else None
+    has_jitter = jitter is not None and jitter.numel() > 0
+    batch = nat.T2NBatch(_ptr(rays), _ptr(jitter) if has_jitter else None, R, S, int(is_train), int(white_bg))
+    outs = nat.T2NOutputs(_ptr(rgb_map), None, _ptr(z_vals), _ptr(weight))
+    scratch = nat.T2NScratch(*[sc[k] if k == "act_rows" else _ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
+    tg = None
+    if trans_grad is not None:
+        assert g_w is None
+        tg = nat.T2NTransGrad(_ptr(trans_grad[0]), _ptr(trans_grad[1]), float(trans_grad[2]))
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.t2n_render_backward_tg(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
+                                        C.byref(batch), C.byref(outs), C.byref(scratch), _ptr(g_rgb), _ptr(g_depth),
+                                        _ptr(g_w), C.byref(tg) if tg is not None else None, C.byref(gstruct), stream)
+    nat.check(rc, "t2n_render_backward")
+    return grads
+
+
 class _RenderFn(torch.autograd.Function):
     """rgb_map, depth_map, z_vals, weight = render(rays; parameters)  via t2n_render_forward /
     t2n_render_backward."""
 
     @staticmethod
     def forward(ctx, model, rays, jitter, n_samples, is_train, white_bg, track_grad, *params):
-        lib = nat.load()
-        dev = rays.device
-        R, S = rays.shape[0], n_samples
         # grad mode is always off inside Function.forward and needs_input_grad ignores no_grad(): the caller
         # passes torch.is_grad_enabled() explicitly
         need_bwd = bool(track_grad) and any(ctx.needs_input_grad[7:])
-        if need_bwd:
-            model._poll_listed_count()
-        p_cl = model._native_param_tensors(params)
-        field = model._native_field()
-        pstruct = model._native_params(p_cl)
-        f32 = dict(device=dev, dtype=torch.float32)
-        i32 = dict(device=dev, dtype=torch.int32)
-        rgb_map = torch.empty((R, 3), **f32)
-        depth_map = torch.empty((R,), **f32)
-        z_vals = torch.empty((R, S), **f32)
-        weight = torch.empty((R, S), **f32)
-        sc = dict(
-            sigma_feat=torch.empty((R, S), **f32) if need_bwd else None,
-            trans=torch.empty((R, S), **f32) if need_bwd else None,
-            acc=torch.empty((R,), **f32), dsum=torch.empty((R,), **f32),
-            ray_start=torch.empty((R,), **i32), ray_count=torch.empty((R,), **i32),
-            slots=torch.empty((R * S,), **i32), app_rgb=torch.empty((R * S, 3), **f32),
-            counters=torch.empty((8,), **i32),
-            w1_packed=model._w1_packed_buffer(dev),
-            ray_flags=torch.empty((R,), **i32),
-            w1_grad_packed=None,
-            mma_pack=model._mma_pack_buffer(dev, field), act_h1_img=None, act_h2_img=None, act_feat=None,
-            act_rows=0, bwd_pack=None, bwd_img=None)
-        if need_bwd and sc["mma_pack"] is not None and int(field.feature_c) == 128:
-            # training state of the tensor-core backward: decoder activations as operand images + features,
-            # sized from the running estimate of listed samples (a batch that overflows it takes the FFMA path)
-            rows = model._act_capacity(R, S)
-            sc["act_rows"] = rows
-            sc["act_h1_img"] = torch.empty((rows * 1024,), device=dev, dtype=torch.uint8)
-            sc["act_h2_img"] = torch.empty((rows * 1024,), device=dev, dtype=torch.uint8)
-            sc["act_feat"] = torch.empty((rows, 32), **f32)
-        mask = model.alphaMask.native() if model.alphaMask is not None else None
-        batch = nat.T2NBatch(_ptr(rays), _ptr(jitter), R, S, int(is_train), int(white_bg))
-        outs = nat.T2NOutputs(_ptr(rgb_map), _ptr(depth_map), _ptr(z_vals), _ptr(weight))
-        scratch = nat.T2NScratch(*[sc[k] if k == "act_rows" else _ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.t2n_render_forward(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
-                                        C.byref(batch), C.byref(outs), C.byref(scratch), stream)
-        nat.check(rc, "t2n_render_forward")
-        model._last_counters = sc["counters"]
-        if need_bwd:
-            model._post_listed_count(sc["counters"])
-        model._last_scratch = sc if os.environ.get("T2N_KEEP_SCRATCH") else None
+        (rgb_map, depth_map, z_vals, weight), sc, p_cl = _render_forward(model, rays, jitter, n_samples, is_train,
+                                                                         white_bg, need_bwd, params)
         if need_bwd:
             ctx.model = model
-            ctx.args = (R, S, bool(is_train), bool(white_bg))
+            ctx.args = (n_samples, bool(is_train), bool(white_bg))
             ctx.scratch = sc
-            ctx.n_params = len(params)
             ctx.save_for_backward(rays, jitter if jitter is not None else rays.new_empty(0), z_vals, weight, rgb_map, *p_cl)
         ctx.mark_non_differentiable(z_vals)
         return rgb_map, depth_map, z_vals, weight
 
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_z, g_w):
-        lib = nat.load()
         model = ctx.model
-        R, S, is_train, white_bg = ctx.args
+        S, is_train, white_bg = ctx.args
         rays, jitter, z_vals, weight, rgb_map, *p_cl = ctx.saved_tensors
-        dev = rays.device
-        sc = ctx.scratch
-        field = model._native_field()
-        pstruct = model._native_params(p_cl)
+        dev, R = rays.device, rays.shape[0]
         g_rgb = (g_rgb if g_rgb is not None else torch.zeros_like(rgb_map)).contiguous().float()
         g_depth = (g_depth if g_depth is not None else torch.zeros((R,), device=dev)).contiguous().float()
         g_w = None if g_w is None else g_w.contiguous().float()
-        grads = model._grad_buffers(p_cl)
-        gstruct = model._native_grads(grads)
-        if model._is_mlp:
-            sc["w1_grad_packed"] = torch.empty_like(sc["w1_packed"])
-        if sc["act_rows"]:
-            npack = int(lib.t2n_bwd_pack_floats(C.byref(field)))
-            row_bytes = int(lib.t2n_bwd_image_row_bytes(C.byref(field)))
-            if npack and row_bytes:
-                sc["bwd_pack"] = torch.empty((npack,), device=dev, dtype=torch.float32)
-                sc["bwd_img"] = torch.empty((sc["act_rows"] * row_bytes,), device=dev, dtype=torch.uint8)
-        mask = model.alphaMask.native() if model.alphaMask is not None else None
-        batch = nat.T2NBatch(_ptr(rays), _ptr(jitter) if jitter.numel() else None, R, S, int(is_train), int(white_bg))
-        outs = nat.T2NOutputs(_ptr(rgb_map), None, _ptr(z_vals), _ptr(weight))
-        scratch = nat.T2NScratch(*[sc[k] if k == "act_rows" else _ptr(sc[k]) for k, _ in nat.T2NScratch._fields_])
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.t2n_render_backward(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
-                                         C.byref(batch), C.byref(outs), C.byref(scratch), _ptr(g_rgb), _ptr(g_depth),
-                                         _ptr(g_w), C.byref(gstruct), stream)
-        nat.check(rc, "t2n_render_backward")
+        grads = _render_backward(model, ctx.scratch, rays, jitter, S, is_train, white_bg, z_vals, weight, rgb_map, p_cl,
+                                 g_rgb, g_depth, g_w)
         ctx.scratch = None
         return (None, None, None, None, None, None, None, *model._grads_for_autograd(grads))
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """loss, l_rgb, l_depth, l_trans = data_loss(render(rays; parameters), rgb_gt, depth_gt): forward render in training
+    mode + the fused loss kernel (t2n_data_loss); backward feeds the loss kernel's gradients -- the weight gradient in
+    compact per-ray form, no [R,S] tensor -- to t2n_render_backward_tg.  Replaces text2nerf_main.py:556-575."""
+
+    @staticmethod
+    def forward(ctx, model, rays, jitter, n_samples, white_bg, rgb_gt, depth_gt, w_depth, w_trans, delta, inv_scale,
+                track_grad, *params):
+        lib = nat.load()
+        need_bwd = bool(track_grad) and any(ctx.needs_input_grad[12:])
+        (rgb_map, depth_map, z_vals, weight), sc, p_cl = _render_forward(model, rays, jitter, n_samples, True, white_bg,
+                                                                         need_bwd, params)
+        dev, R, S = rays.device, rays.shape[0], n_samples
+        f32 = dict(device=dev, dtype=torch.float32)
+        terms = torch.empty((R, 3), **f32)
+        g_rgb, g_depth, gw_coef = torch.empty((R, 3), **f32), torch.empty((R,), **f32), torch.empty((R,), **f32)
+        outs = nat.T2NOutputs(_ptr(rgb_map), _ptr(depth_map), _ptr(z_vals), _ptr(weight))
+        with torch.cuda.device(dev):
+            rc = lib.t2n_data_loss(C.byref(outs), R, S, _ptr(rgb_gt), _ptr(depth_gt), float(w_depth), float(w_trans),
+                                   float(delta), float(inv_scale), _ptr(terms), _ptr(g_rgb), _ptr(g_depth), _ptr(gw_coef),
+                                   None, torch.cuda.current_stream(dev).cuda_stream)
+        nat.check(rc, "t2n_data_loss")
+        sums = terms.sum(0) * inv_scale
+        l_rgb, l_depth, l_trans = sums[0] / 3.0, sums[1], sums[2]
+        loss = l_rgb + w_depth * l_depth + w_trans * l_trans
+        if need_bwd:
+            ctx.model = model
+            ctx.args = (n_samples, bool(white_bg), float(delta))
+            ctx.scratch = sc
+            ctx.save_for_backward(rays, jitter if jitter is not None else rays.new_empty(0), z_vals, weight, rgb_map,
+                                  g_rgb, g_depth, gw_coef, depth_gt, *p_cl)
+        ctx.mark_non_differentiable(l_rgb, l_depth, l_trans)
+        return loss, l_rgb, l_depth, l_trans
+
+    @staticmethod
+    def backward(ctx, g_loss, *_unused):
+        model = ctx.model
+        S, white_bg, delta = ctx.args
+        rays, jitter, z_vals, weight, rgb_map, g_rgb, g_depth, gw_coef, depth_gt, *p_cl = ctx.saved_tensors
+        # the loss is a scalar: its incoming gradient scales the three per-ray gradients (1.0 for loss.backward())
+        g = g_loss.to(torch.float32)
+        grads = _render_backward(model, ctx.scratch, rays, jitter, S, True, white_bg, z_vals, weight, rgb_map, p_cl,
+                                 g_rgb * g, g_depth * g, None, trans_grad=(gw_coef * g, depth_gt, delta))
+        ctx.scratch = None
+        return (None,) * 12 + tuple(model._grads_for_autograd(grads))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -601,6 +670,40 @@ class TensorBase(torch.nn.Module):
             for lst, t in zip(outs, part):
                 lst.append(t)
         return tuple(torch.cat(x) for x in outs)
+
+    def data_loss(self, rays_chunk, rgb_gt, depth_gt, white_bg=True, N_samples=-1, w_depth=0.005, w_trans=1e3,
+                  delta=0.1, n_rays_total=None, return_terms=False):
+        """Fused fast path of one training step's data terms (text2nerf_main.py:556-575):
+
+            rgb_map, _, depth_map, weights, z_vals = renderer(rays, tensorf, ..., is_train=True)
+            depth_map = where(isnan(depth_map), 0, depth_map)
+            loss = mean((rgb_map - rgb)^2) + w_depth * mean((depth_map - depth)^2)
+                 + w_trans * TransMittanceLoss_mask(weights, (z_vals - depth[:, None] + delta) < 0)
+
+        as ONE differentiable scalar: forward render, loss kernel and (on .backward()) the backward kernels, without
+        the ~100 small tensor kernels of the composed expression and without an [R,S] weight-gradient tensor.  Draws
+        the same CPU random numbers as forward(is_train=True).  n_rays_total: number of rays the means run over when
+        this call holds one shard of a ray-sharded batch (default: this chunk).  return_terms adds the three
+        unweighted terms (detached) for logging."""
+        if self.shadingMode == 'MLP_PE':
+            raise RuntimeError("MLP_PE is not runnable in the reference either (tensorBase.py:115 vs :124-130)")
+        if not rays_chunk.is_cuda:
+            raise nat.NativeLibraryError("text2nerf_b200 renders on a CUDA device only; rays are on " + str(rays_chunk.device))
+        rays = rays_chunk.detach()[..., :6].float().contiguous()
+        if rays.dim() != 2 or rays.shape[-1] != 6:
+            raise ValueError("rays_chunk must be [R,6+] (origin, direction)")
+        R = rays.shape[0]
+        S = int(N_samples) if N_samples > 0 else self.nSamples
+        if R > ((1 << 31) - 1) // S:
+            raise ValueError("data_loss takes one training batch; split larger ray sets")
+        rgb_gt = rgb_gt.detach().to(rays.device, torch.float32).reshape(R, 3).contiguous()
+        depth_gt = depth_gt.detach().to(rays.device, torch.float32).reshape(R).contiguous()
+        jitter = torch.rand(R, 1).to(rays.device, non_blocking=True).view(-1)       # tensorBase.py:313-317
+        white = bool(white_bg) or bool(torch.rand((1,)) < 0.5)                       # tensorBase.py:497
+        inv_scale = 1.0 / float(n_rays_total if n_rays_total else R)
+        out = _FusedLossFn.apply(self, rays, jitter, S, white, rgb_gt, depth_gt, float(w_depth), float(w_trans),
+                                 float(delta), inv_scale, torch.is_grad_enabled(), *self._flat_params())
+        return out if return_terms else out[0]
 
     # ---- native glue (overridden / completed by TensorVMSplit) ------------------------------------
     @property
