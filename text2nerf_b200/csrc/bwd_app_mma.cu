@@ -9,9 +9,10 @@ int launch_pack_bwd(const BwdPackArgs& a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 int launch_app_backward_mma(const BwdMmaArgs& a, int smem_bytes, int grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(app_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    auto kern = a.trace != nullptr ? app_backward_mma_kernel<true> : app_backward_mma_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return (int)e;
-    app_backward_mma_kernel<<<grid, kMmaThreads, smem_bytes, st>>>(a);
+    kern<<<grid, kMmaThreads, smem_bytes, st>>>(a);
     return (int)cudaGetLastError();
 }
 int launch_wgrad(WgradArgs& a, int max_smem, int grid, cudaStream_t st) {

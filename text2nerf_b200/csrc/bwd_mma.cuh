@@ -81,6 +81,7 @@ static __global__ void pack_bwd_weights_kernel(const __grid_constant__ BwdPackAr
     *reinterpret_cast<float4*>(dst_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
+template <bool TR>
 __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const __grid_constant__ BwdMmaArgs args) {
     extern __shared__ uint8_t smem_raw[];
     const AppArgs& a = args.fw;
@@ -246,10 +247,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a);
         };
-        const bool tr = args.trace != nullptr && blockIdx.x == 0 && tid == 0;
+        // phase cycle counters exist only in the trace instantiation (T2N_BWD_TRACE): in the production kernel they were
+        // local-memory traffic in front of every phase
+        const bool tr = TR && args.trace != nullptr && blockIdx.x == 0 && tid == 0;
         long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        long long tlast = clock64();
-        auto mark = [&](int ph) { const long long tt = clock64(); tph[ph] += tt - tlast; tlast = tt; };
+        long long tlast = TR ? clock64() : 0;
+        auto mark = [&](int ph) { if (TR) { const long long tt = clock64(); tph[ph] += tt - tlast; tlast = tt; } };
         // this thread's 8 base-vector entries (slot s = 8q + i) and their PE frequency counts
         int own[8], nf[8];
 #pragma unroll
