@@ -39,8 +39,8 @@ def main():
     g = torch.Generator().manual_seed(0)
     for _ in range(a.train_batches):
         idx = torch.randint(0, rays.shape[0], (a.batch,), generator=g).to(dev)
-        out = model(rays[idx].contiguous(), is_train=True, white_bg=True, N_samples=S)
-        loss = orc.training_loss(*out, torch.rand(a.batch, 3, generator=g).to(dev), (2 + 4 * torch.rand(a.batch, generator=g)).to(dev))
+        loss = model.data_loss(rays[idx].contiguous(), torch.rand(a.batch, 3, generator=g).to(dev),
+                               (2 + 4 * torch.rand(a.batch, generator=g)).to(dev), white_bg=True, N_samples=S)
         loss.backward()
     torch.cuda.synchronize()
     print("done", model.app_sample_count())
