@@ -463,25 +463,22 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
             if (ok1) {
                 ev(tr_j, tr_ci, 0);
                 acc_wait(0, j - 1);
-                if (warp < 4) {
-                    uint32_t v[16];
+                {
+                    // every warp moves the 8 feature columns of its column quarter (balanced: nobody waits at the barrier
+                    // below for four warps doing all 32)
+                    uint32_t v[8];
                     float* bw = base + erow * kBaseStride;
-                    tmem_ld16(tmem + tmem_lane + kColD0, v);
+                    tmem_ld8(tmem + tmem_lane + kColD0 + 8 * eq, v);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) if (q < a.app_dim) bw[q] = __uint_as_float(v[q]);
-                    tmem_ld16(tmem + tmem_lane + kColD0 + 16, v);
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) if (16 + q < a.app_dim) bw[16 + q] = __uint_as_float(v[q]);
+                    for (int q = 0; q < 8; ++q) if (8 * eq + q < a.app_dim) bw[8 * eq + q] = __uint_as_float(v[q]);
                     const int e_feat = (blockIdx.x + (j - 1) * gridDim.x) * kMmaM + erow;
                     if (args.feat != nullptr && e_feat < args.act_rows) {       // feature vector for the backward's PE chain
-                        float4* dst = reinterpret_cast<float4*>(args.feat + (size_t)e_feat * 32);
+                        float4* dst = reinterpret_cast<float4*>(args.feat + (size_t)e_feat * 32) + 2 * eq;
+                        float f8[8];
 #pragma unroll
-                        for (int q4 = 0; q4 < 8; ++q4) {
-                            float f4v[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) f4v[u] = (4 * q4 + u < a.app_dim) ? bw[4 * q4 + u] : 0.f;
-                            dst[q4] = make_float4(f4v[0], f4v[1], f4v[2], f4v[3]);
-                        }
+                        for (int q = 0; q < 8; ++q) f8[q] = (8 * eq + q < a.app_dim) ? __uint_as_float(v[q]) : 0.f;
+                        dst[0] = make_float4(f8[0], f8[1], f8[2], f8[3]);
+                        dst[1] = make_float4(f8[4], f8[5], f8[6], f8[7]);
                     }
                 }
                 tc_fence_before();
@@ -648,7 +645,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                         a.app_rgb[(size_t)e * 3 + c] = 1.f / (1.f + expf(-sres));
                     }
                 }
-                producers_sync();
+                // `part` is rewritten by the next iteration's S3; the barrier of its S1 chunk 0 separates the two unless that
+                // iteration has no S1 (drain iterations)
+                if (j >= n_tiles) producers_sync();
             }
             tmark(kStepS3, ts0);
         }

@@ -61,3 +61,17 @@ for jj in range(NJ):
             ci, min(st) - t0 if st else -1, max(st) - t0 if st else -1, min(st3) - t0 if st3 else -1, max(st3) - t0 if st3 else -1,
             min(rd) - t0 if rd else -1, max(rd) - t0 if rd else -1, min(pb) - t0, max(pb) - t0,
             E(16, jj, ci, 0) - t0, E(16, jj, ci, 1) - t0, E(16, jj, ci, 2) - t0, E(17, jj, ci, 0) - t0))
+
+# per-warp lateness: mean over chunks of (publish time of the warp - earliest publish of the chunk)
+late = [0.0] * 16
+cnt = 0
+for jj in range(NJ):
+    for ci in range(22):
+        pb = [E(w, jj, ci, 2) for w in range(16)]
+        if min(pb) <= 0:
+            continue
+        m0 = min(pb)
+        for w in range(16):
+            late[w] += pb[w] - m0
+        cnt += 1
+print("mean publish lateness per producer warp (cycles):", " ".join("%d:%.0f" % (w, late[w] / max(cnt, 1)) for w in range(16)))
