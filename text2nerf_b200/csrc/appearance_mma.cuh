@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                     const int kind = prog[s] & 7, idx = prog[s] >> 3;
                     if (!is_chunk(kind, idx) || !step_ok(j, kind)) continue;
                     const uint32_t bs = loaded % kNB;
-                    if (loaded >= kNB) mbar_wait(bar_done + bs, ((loaded / kNB) - 1) & 1);
+                    if (loaded >= kNB) mbar_wait_hint(bar_done + bs, ((loaded / kNB) - 1) & 1, 2000u);
                     ev(j, ci++, 0);
                     const float* src; uint32_t bytes;
                     if (kind == kStepU) { src = args.pack + P.basis_off + (size_t)(idx >> 1) * 2 * 32 * 32; bytes = 2 * 32 * 128; }
@@ -246,10 +246,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                     const uint32_t bs = it % kNB;
                     long long c0 = 0, c1 = 0, c2 = 0;
                     if (TR) c0 = clock64();
-                    mbar_wait(bar_bfull + bs, (it / kNB) & 1);
+                    mbar_wait_hint(bar_bfull + bs, (it / kNB) & 1, 2000u);
                     if (TR) c1 = clock64();
                     ev(j, ci, 0);
-                    mbar_wait(bar_afull + (it & 3), (it >> 2) & 1);
+                    mbar_wait_hint(bar_afull + (it & 3), (it >> 2) & 1, 2000u);
                     if (TR) c2 = clock64();
                     ev(j, ci, 1);
                     tc_fence_after();

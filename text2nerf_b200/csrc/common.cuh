@@ -202,6 +202,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "T2N_DONE_%=:\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same with a suspend-time hint: the hardware parks the warp until the phase completes or `ns` have passed instead of
+// returning immediately, so a waiting issuer / loader warp does not take issue slots from the producer warps that share
+// its scheduler.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "T2N_WAITH_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra T2N_DONEH_%=;\n\t"
+        "bra T2N_WAITH_%=;\n\t"
+        "T2N_DONEH_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+}
 // Same, for waits that are expected to take long (producer warps waiting for MMA completion): back off between
 // polls so that 16 spinning warps do not compete with the tensor core's operand reads for shared memory.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
