@@ -365,6 +365,51 @@ def main():
         bk = dict(nat.profile_read())
         lib.t2n_profile_enable(0)
         fwd_bwd["kernel_ms"] = {**fk, **bk}
+        # ---- the whole training iteration of text2nerf_main.py:547-598: data loss + TV regularisers + Adam
+        # (TV_weight_density 0.1, TV_weight_app 0.01, configs/text2nerf_scenes.txt:31-32), fused against composed
+        from text2nerf_b200.optim import FusedAdam
+
+        class TVLoss(torch.nn.Module):          # the reference's utils.TVLoss (utils.py:488-504) as the loop passes it
+            TVLoss_weight = 1
+
+            def forward(self, x):
+                return self.TVLoss_weight * orc.tv_plane(x)
+
+        tvreg = TVLoss()
+
+        def make_iteration(fused):
+            opt = (FusedAdam if fused else torch.optim.Adam)(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+            reg = tvreg if fused else tvreg.forward      # a plain callable takes the tensor-op route
+
+            def iteration():
+                for rays_b, rgb_gt, depth_gt in batches:
+                    flat.zero_()
+                    if fused:
+                        total = model.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S)
+                    else:
+                        total = orc.training_loss(*model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S),
+                                                  rgb_gt, depth_gt)
+                    total = total + model.TV_loss_density(reg) * 0.1 + model.TV_loss_app(reg) * 0.01
+                    total.backward()
+                    t2n_dist.allreduce_flat_grads(model, world)
+                    t2n_dist.attach_flat_grads(model)
+                    opt.step()
+            return iteration
+
+        state0 = {k: v.detach().clone(memory_format=torch.preserve_format) for k, v in model.state_dict().items()}
+        full = {}
+        for tag, fused in (("fused", True), ("composed", False)):
+            it_fn = make_iteration(fused)
+            it_fn()
+            ms_it = timed(it_fn, 2)
+            full[tag + "_ms_per_iteration"] = ms_it / (2 * TRAIN_BATCHES_PER_STEP)
+            for p_ in model.parameters():
+                p_.grad = None
+            model.load_state_dict(state0)
+        full["what"] = ("one iteration of text2nerf_main.py:547-598 on a 4096-ray batch: data loss fwd+bwd, TV_loss_density*0.1 + "
+                        "TV_loss_app*0.01, Adam step; fused = data_loss + t2n_tv_* + FusedAdam, composed = tensor-op loss and "
+                        "TV on the same render kernels + torch.optim.Adam")
+        fwd_bwd["full_iteration"] = full
         launches_train = 16 * TRAIN_BATCHES_PER_STEP * args.steps    # march, pack, app, finalize, data_loss | pack_bwd, bwd-data, 4 wgrad, (pack_w1, ffma fallback, unpack: early exit), ray_backward
         model.enable_flat_grads(False)
 

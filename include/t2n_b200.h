@@ -250,6 +250,33 @@ int t2n_data_loss(const T2NOutputs* out, int R, int S, const float* rgb_gt, cons
                   float* ray_terms, float* g_rgb_map, float* g_depth_map, float* gw_coef, float* g_weight_dense,
                   t2n_stream_t stream);
 
+/* One Adam step over a list of parameter tensors in a single launch (the optimiser of the training loop,
+ * torch.optim.Adam(grad_vars, betas=(0.9, 0.99)), text2nerf_main.py:453-454, :589).  Arithmetic of
+ * torch.optim.Adam without amsgrad/maximize; `step` is the 1-based step count t of the bias corrections.  Every tensor is
+ * raw device memory of numel floats: param / grad / exp_avg / exp_avg_sq of one tensor must share one dense layout.
+ * `tensors` is a HOST array. */
+typedef struct T2NAdamTensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    long long numel;
+    float lr;
+} T2NAdamTensor;
+int t2n_adam_step(const T2NAdamTensor* tensors, int n_tensors, float beta1, float beta2, float eps, float weight_decay,
+                  int step, t2n_stream_t stream);
+
+/* Total-variation regulariser of one VM plane, utils.TVLoss (utils.py:488-504) as TV_loss_density / TV_loss_app use it
+ * (models/tensoRF.py:193-203).  plane is [H][W][C] in memory (channels_last [1,C,H,W]), C % 4 == 0.
+ * t2n_tv_plane_sums writes per-block partial sums partials[t2n_tv_blocks()][2] = (sum of squared differences along H,
+ * along W); the caller adds them up: tv = w * 2 * (sum_h / (C*(H-1)*W) + sum_w / (C*H*(W-1))).
+ * t2n_tv_plane_grad accumulates grad += g_out[0] * (coef_h * d(sum_h)/dx + coef_w * d(sum_w)/dx), g_out a DEVICE scalar
+ * (the incoming gradient of the loss term), coef_* = w * 2 * 1e-2 / count_* for TV_loss_density / TV_loss_app. */
+int t2n_tv_blocks(void);
+int t2n_tv_plane_sums(const float* plane, int H, int W, int C, float* partials, t2n_stream_t stream);
+int t2n_tv_plane_grad(const float* plane, int H, int W, int C, const float* g_out, float coef_h, float coef_w,
+                      float* grad, t2n_stream_t stream);
+
 /* Camera rays of one view: get_ray_directions (+ optional per-pixel normalisation as
  * dataLoader/scene_gen.py:45 applies) followed by get_rays (dataLoader/ray_utils.py:24-42,
  * 66-87).  c2w is a HOST pointer to 12 floats (row-major 3x4).  rays [H*W][6]. */

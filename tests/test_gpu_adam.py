@@ -1,0 +1,61 @@
+"""FusedAdam (t2n_adam_step) against torch.optim.Adam on the model's own parameter groups: same trajectories over several
+steps with the in-place lr decay of the training loop (text2nerf_main.py:597-598), channels_last planes, flat-buffer grads."""
+import pytest
+import torch
+
+from helpers import Case, build_model, fused_loss_with_jitter, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fused_adam_follows_torch_adam(cuda_device):
+    from text2nerf_b200.optim import FusedAdam
+    c = Case("t2n_noview_train")
+    a = build_model(c.spec, c.params, cuda_device, c.alpha)
+    b = build_model(c.spec, c.params, cuda_device, c.alpha)
+    oa = FusedAdam(a.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+    ob = torch.optim.Adam(b.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+    rays = c.rays.to(cuda_device)
+    for it in range(4):
+        for model, opt in ((a, oa), (b, ob)):
+            opt.zero_grad()
+            fused_loss_with_jitter(model, rays, c.jitter, c.white_eff, c.n_samples, c.rgb_gt, c.depth_gt)[0].backward()
+            opt.step()
+            for g in opt.param_groups:
+                g["lr"] = g["lr"] * 0.9
+    torch.cuda.synchronize()
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert scaled_err(pa, pb) <= 2e-5, (k, scaled_err(pa, pb))
+        # the update is visible: parameters moved away from the initial state
+    moved = sum(float((p.detach().cpu() - c.params[k]).abs().max()) > 0 for k, p in a.named_parameters())
+    assert moved == len(c.params)
+    sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
+    assert set(sa[0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and int(sa[0]["step"]) == int(sb[0]["step"]) == 4
+    assert scaled_err(sa[0]["exp_avg_sq"], sb[0]["exp_avg_sq"]) <= 1e-5
+
+
+def test_fused_adam_single_step_is_exact_to_rounding_and_rejects_cpu(cuda_device):
+    from text2nerf_b200 import _native as nat
+    from text2nerf_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(1, 16, 33, 21), (7,), (128, 351), (3,)]
+    pa = [torch.randn(s, generator=g).to(cuda_device) for s in shapes]
+    pa[0] = pa[0].contiguous(memory_format=torch.channels_last)
+    pb = [p.clone(memory_format=torch.preserve_format) for p in pa]
+    grads = [torch.randn(s, generator=g).to(cuda_device) for s in shapes]
+    grads[0] = grads[0].contiguous(memory_format=torch.channels_last)
+    for ps in (pa, pb):
+        for p, gr in zip(ps, grads):
+            p.requires_grad_()
+            p.grad = gr.clone(memory_format=torch.preserve_format)
+    oa = FusedAdam([{"params": pa[:2], "lr": 0.02}, {"params": pa[2:], "lr": 0.001}], betas=(0.9, 0.99), weight_decay=0.01)
+    ob = torch.optim.Adam([{"params": pb[:2], "lr": 0.02}, {"params": pb[2:], "lr": 0.001}], betas=(0.9, 0.99), weight_decay=0.01)
+    for _ in range(3):
+        oa.step(); ob.step()
+    torch.cuda.synchronize()
+    for x, y in zip(pa, pb):
+        assert scaled_err(x, y) <= 2e-6
+    cpu = torch.nn.Parameter(torch.zeros(4))
+    cpu.grad = torch.ones(4)
+    with pytest.raises(nat.NativeLibraryError):
+        FusedAdam([cpu]).step()

@@ -76,6 +76,11 @@ class T2NTransGrad(C.Structure):
     _fields_ = [("coef", C.c_void_p), ("depth_gt", C.c_void_p), ("delta", C.c_float)]
 
 
+class T2NAdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_longlong), ("lr", C.c_float)]
+
+
 class T2NScratch(C.Structure):
     _fields_ = [("sigma_feat", C.c_void_p), ("trans", C.c_void_p), ("acc", C.c_void_p),
                 ("dsum", C.c_void_p), ("ray_start", C.c_void_p), ("ray_count", C.c_void_p),
@@ -109,6 +114,12 @@ SYMBOLS = {
     "t2n_data_loss": (C.c_int, [C.POINTER(T2NOutputs), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "t2n_adam_step": (C.c_int, [C.POINTER(T2NAdamTensor), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                C.c_void_p]),
+    "t2n_tv_blocks": (C.c_int, []),
+    "t2n_tv_plane_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "t2n_tv_plane_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float,
+                                    C.c_void_p, C.c_void_p]),
     "t2n_get_rays": (C.c_int, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "t2n_rotate_rays": (C.c_int, [C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -153,7 +164,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
 
 
 KERNEL_NAMES = {0: "march", 1: "pack_w1", 2: "appearance", 3: "finalize", 4: "app_backward_ffma",
-                5: "unpack_w1_grad", 6: "ray_backward", 7: "pack_bwd", 8: "app_backward_mma", 9: "wgrad", 10: "data_loss"}
+                5: "unpack_w1_grad", 6: "ray_backward", 7: "pack_bwd", 8: "app_backward_mma", 9: "wgrad", 10: "data_loss", 11: "tv_sums", 12: "tv_grad", 13: "adam"}
 
 
 def profile_read():

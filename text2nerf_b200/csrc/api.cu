@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <cmath>
 #include "launch.h"
 #include "rays.cuh"
 
@@ -359,6 +360,71 @@ int t2n_data_loss(const T2NOutputs* out, int R, int S, const float* rgb_gt, cons
     a.ray_terms = ray_terms; a.g_rgb = g_rgb_map; a.g_depth = g_depth_map; a.gw_coef = gw_coef; a.g_weight = g_weight_dense;
     g_prof.start(10, reinterpret_cast<cudaStream_t>(stream));
     const int rc = launch_data_loss(a, reinterpret_cast<cudaStream_t>(stream));
+    g_prof.stop(reinterpret_cast<cudaStream_t>(stream));
+    return rc;
+}
+
+int t2n_adam_step(const T2NAdamTensor* tensors, int n_tensors, float beta1, float beta2, float eps, float weight_decay,
+                  int step, t2n_stream_t stream) {
+    if (!tensors || n_tensors < 0 || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f))
+        return T2N_E_BADARG;
+    DeviceInfo& dev = device_info();
+    if (!dev.ok || dev.cc_major != 10) return T2N_E_DEVICE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    g_prof.start(13, st);
+    int rc = 0;
+    for (int first = 0; first < n_tensors && rc == 0; first += kAdamMaxTensors) {
+        AdamTable a;
+        memset(&a, 0, sizeof(a));
+        const int cnt = n_tensors - first < kAdamMaxTensors ? n_tensors - first : kAdamMaxTensors;
+        long long chunks = 0;
+        for (int i = 0; i < cnt; ++i) {
+            const T2NAdamTensor& t = tensors[first + i];
+            if (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq || t.numel < 0) return T2N_E_BADARG;
+            a.p[i] = t.param; a.g[i] = t.grad; a.m[i] = t.exp_avg; a.v[i] = t.exp_avg_sq; a.n[i] = t.numel; a.lr[i] = t.lr;
+            a.chunk_begin[i] = (int)chunks;
+            chunks += (t.numel + kAdamChunk - 1) / kAdamChunk;
+            if (chunks > 0x7fffffffLL) return T2N_E_BADARG;
+        }
+        a.chunk_begin[cnt] = (int)chunks;
+        a.n_tensors = cnt;
+        a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+        a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+        a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+        rc = launch_adam(a, st);
+    }
+    g_prof.stop(st);
+    return rc;
+}
+
+int t2n_tv_blocks(void) {
+    DeviceInfo& dev = device_info();
+    return dev.ok ? dev.sm_count * 8 : 0;
+}
+
+int t2n_tv_plane_sums(const float* plane, int H, int W, int C, float* partials, t2n_stream_t stream) {
+    if (!plane || !partials || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return T2N_E_BADARG;
+    DeviceInfo& dev = device_info();
+    if (!dev.ok || dev.cc_major != 10) return T2N_E_DEVICE;
+    TvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = plane; a.H = H; a.W = W; a.C = C; a.partials = partials;
+    g_prof.start(11, reinterpret_cast<cudaStream_t>(stream));
+    const int rc = launch_tv_sums(a, t2n_tv_blocks(), reinterpret_cast<cudaStream_t>(stream));
+    g_prof.stop(reinterpret_cast<cudaStream_t>(stream));
+    return rc;
+}
+
+int t2n_tv_plane_grad(const float* plane, int H, int W, int C, const float* g_out, float coef_h, float coef_w,
+                      float* grad, t2n_stream_t stream) {
+    if (!plane || !grad || !g_out || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return T2N_E_BADARG;
+    DeviceInfo& dev = device_info();
+    if (!dev.ok || dev.cc_major != 10) return T2N_E_DEVICE;
+    TvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = plane; a.H = H; a.W = W; a.C = C; a.g_out = g_out; a.coef_h = coef_h; a.coef_w = coef_w; a.grad = grad;
+    g_prof.start(12, reinterpret_cast<cudaStream_t>(stream));
+    const int rc = launch_tv_grad(a, t2n_tv_blocks(), reinterpret_cast<cudaStream_t>(stream));
     g_prof.stop(reinterpret_cast<cudaStream_t>(stream));
     return rc;
 }

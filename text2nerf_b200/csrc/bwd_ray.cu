@@ -23,4 +23,18 @@ int launch_data_loss(const DataLossArgs& a, cudaStream_t st) {
     data_loss_kernel<<<grid, 256, 0, st>>>(a);
     return (int)cudaGetLastError();
 }
+int launch_tv_sums(const TvArgs& a, int grid, cudaStream_t st) {
+    tv_sums_kernel<<<grid, 256, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+int launch_tv_grad(const TvArgs& a, int grid, cudaStream_t st) {
+    tv_grad_kernel<<<grid, 256, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+int launch_adam(const AdamTable& a, cudaStream_t st) {
+    const int grid = a.chunk_begin[a.n_tensors];
+    if (grid <= 0) return 0;
+    adam_kernel<<<grid, 256, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
 }  // namespace t2n

@@ -7,6 +7,8 @@
 #include "appearance_mma_defs.cuh"
 #include "bwd_mma_defs.cuh"
 #include "loss.cuh"
+#include "tv.cuh"
+#include "adam.cuh"
 
 
 namespace t2n {
@@ -22,6 +24,9 @@ int launch_unpack_w1_grad(const float* gw1p, const int32_t* perm, int C, int K, 
 int launch_pack_bwd(const BwdPackArgs& a, cudaStream_t st);
 int launch_app_backward_mma(const BwdMmaArgs& a, int smem_bytes, int grid, cudaStream_t st);
 int launch_wgrad(WgradArgs& a, int max_smem, int grid, cudaStream_t st);
+int launch_tv_sums(const TvArgs& a, int grid, cudaStream_t st);
+int launch_tv_grad(const TvArgs& a, int grid, cudaStream_t st);
+int launch_adam(const AdamTable& a, cudaStream_t st);
 int launch_data_loss(const DataLossArgs& a, cudaStream_t st);
 int launch_make_image(const float* rows, int n_rows, int ng, uint8_t* img, cudaStream_t st);
 }  // namespace t2n

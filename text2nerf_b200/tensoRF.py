@@ -24,6 +24,57 @@ from .tensorBase import (AlphaGridMask, TensorBase, _texel_major, positional_enc
 _CL = torch.channels_last
 
 
+class _TVFn(torch.autograd.Function):
+    """sum_i TVLoss(w)(plane_i) * 1e-2 over the three planes of one factor family through t2n_tv_plane_sums /
+    t2n_tv_plane_grad (csrc/tv.cuh).  The gradient pass accumulates straight into the model's gradient buffers: the flat
+    all-reduce buffer when enable_flat_grads() is on (autograd then gets nothing, like the render backward)."""
+
+    @staticmethod
+    def forward(ctx, model, weight, first_index, track_grad, *planes):
+        lib = nat.load()
+        dev = planes[0].device
+        blocks = int(lib.t2n_tv_blocks())
+        cl = [_texel_major(p.detach()) for p in planes]
+        partials = torch.empty((len(cl), blocks, 2), device=dev, dtype=torch.float32)
+        scales = []
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for i, t in enumerate(cl):
+                _, C, H, W = t.shape
+                nat.check(lib.t2n_tv_plane_sums(t.data_ptr(), H, W, C, partials[i].data_ptr(), stream), "t2n_tv_plane_sums")
+                # TVLoss: weight * 2 * (h_tv / count_h + w_tv / count_w) / batch, times the 1e-2 of TV_loss_*
+                scales.append([weight * 2.0 * 1e-2 / (C * (H - 1) * W), weight * 2.0 * 1e-2 / (C * H * (W - 1))])
+        cache = model.__dict__.setdefault("_tv_scale_cache", {})
+        key = (first_index, weight, tuple(tuple(t.shape) for t in cl), str(dev))
+        if key not in cache:            # device copy of the per-plane normalisations, made once per configuration
+            cache[key] = torch.tensor(scales, dtype=torch.float32).to(dev)
+        loss = (partials.sum(1) * cache[key]).sum()
+        if track_grad and any(ctx.needs_input_grad[4:]):
+            ctx.model, ctx.first_index, ctx.scales = model, first_index, scales
+            ctx.save_for_backward(*cl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        lib = nat.load()
+        cl = ctx.saved_tensors
+        model = ctx.model
+        dev = cl[0].device
+        flat = getattr(model, "_flat_grad", None)
+        if flat is not None:
+            dests = flat["views"][ctx.first_index:ctx.first_index + len(cl)]
+        else:
+            dests = [torch.zeros_like(t) for t in cl]
+        g = g_loss.detach().to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for t, d, (ch, cw) in zip(cl, dests, ctx.scales):
+                _, C, H, W = t.shape
+                nat.check(lib.t2n_tv_plane_grad(t.data_ptr(), H, W, C, g.data_ptr(), ch, cw, d.data_ptr(), stream),
+                          "t2n_tv_plane_grad")
+        return (None, None, None, None) + ((None,) * len(cl) if flat is not None else tuple(dests))
+
+
 def _as_list3(n) -> List[int]:
     return [int(n)] * 3 if isinstance(n, int) else [int(v) for v in n]
 
@@ -99,16 +150,25 @@ class TensorVMSplit(TensorBase):
         return total
 
     def TV_loss_density(self, reg):
-        total = 0
-        for plane in self.density_plane:
-            total = total + reg(plane) * 1e-2
-        return total
+        """sum_i reg(density_plane[i]) * 1e-2 (tensoRF.py:193-197).  With the reference's utils.TVLoss as `reg` and the
+        planes on a CUDA device this runs the fused TV kernels (one read pass for the value, one read + accumulate pass
+        for the gradient); any other callable is applied to the planes as tensor ops."""
+        return self._tv_loss(reg, list(self.density_plane), 0)
 
     def TV_loss_app(self, reg):
-        total = 0
-        for plane in self.app_plane:
-            total = total + reg(plane) * 1e-2
-        return total
+        """sum_i reg(app_plane[i]) * 1e-2 (tensoRF.py:199-203); see TV_loss_density."""
+        return self._tv_loss(reg, list(self.app_plane), 6)
+
+    def _tv_loss(self, reg, planes, first_index):
+        w = getattr(reg, "TVLoss_weight", None)
+        fused = (w is not None and type(reg).__name__ == "TVLoss" and all(p.is_cuda and p.dtype == torch.float32 for p in planes)
+                 and all(p.shape[0] == 1 and p.shape[1] % 4 == 0 and p.shape[2] > 1 and p.shape[3] > 1 for p in planes))
+        if not fused:
+            total = 0
+            for plane in planes:
+                total = total + reg(plane) * 1e-2
+            return total
+        return _TVFn.apply(self, float(w), first_index, torch.is_grad_enabled(), *planes)
 
     # ---- factor lookups as tensor ops (API parity; the render path gathers inside the kernels) -----
     def _vm_grids(self, xyz_sampled):
