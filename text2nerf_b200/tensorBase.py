@@ -272,7 +272,7 @@ def _render_forward(model, rays, jitter, n_samples, is_train, white_bg, need_bwd
     nat.check(rc, "t2n_render_forward")
     model._last_counters = sc["counters"]
     if need_bwd:
-        model._post_listed_count(sc["counters"])
+        model._post_listed_count(sc["counters"], R)
     model._last_scratch = sc if os.environ.get("T2N_KEEP_SCRATCH") else None
     return (rgb_map, depth_map, z_vals, weight), sc, p_cl
 
@@ -777,12 +777,13 @@ class TensorBase(torch.nn.Module):
     # memory; later forwards fold completed copies into a running maximum that sizes the next allocation.
     def _act_capacity(self, R, S):
         import os
-        seen = getattr(self, "_listed_seen", 0)
-        rows = max(int(1.25 * seen) + 1024, 48 * R, 8192) if seen else max(96 * R, 8192)
+        # listed samples PER RAY seen recently (decaying maximum), so that a change of batch size scales the estimate
+        per_ray = getattr(self, "_listed_per_ray", 0.0)
+        rows = max(int(1.25 * per_ray * R) + 1024, 8192) if per_ray > 0 else max(96 * R, 8192)
         rows = min(rows, R * S, int(os.environ.get("T2N_ACT_ROWS_MAX", 6 << 20)))
         return max(128, (rows + 127) // 128 * 128)
 
-    def _post_listed_count(self, counters):
+    def _post_listed_count(self, counters, R):
         pend = getattr(self, "_listed_pending", None)
         if pend is None:
             pend = self._listed_pending = []
@@ -795,13 +796,13 @@ class TensorBase(torch.nn.Module):
         host, ev = pool.pop(0)
         host.copy_(counters, non_blocking=True)
         ev.record()
-        pend.append((host, ev))
+        pend.append((host, ev, max(1, int(R))))
 
     def _poll_listed_count(self):
         pend = getattr(self, "_listed_pending", None)
         while pend and pend[0][1].query():
-            host, ev = pend.pop(0)
-            self._listed_seen = max(int(0.98 * getattr(self, "_listed_seen", 0)), int(host[0]))
+            host, ev, n_rays = pend.pop(0)
+            self._listed_per_ray = max(0.98 * getattr(self, "_listed_per_ray", 0.0), float(host[0]) / n_rays)
             self._listed_pool.append((host, ev))
 
     def _w1_packed_buffer(self, device):
