@@ -527,7 +527,7 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
             WgradArgs w;
             auto base = [&](const uint8_t* x, int ngx, const uint8_t* y, int ngy, float* o, float* ones) {
                 memset(&w, 0, sizeof(w));
-                w.x_img = x; w.ngx = ngx; w.y_img = y; w.ngy = ngy; w.counters = scratch->counters; w.cap_rows = cap_rows;
+                w.x_img = x; w.ngx = ngx; w.y_img = y; w.ngy = ngy; w.counters = scratch->counters; w.cap_rows = cap_rows; w.clamp = 1;
                 w.terms = d.terms; w.out = o; w.ones_out = ones;
                 for (int i = 0; i < 128; ++i) { w.row_off[i] = -1; w.row_off_ones[i] = -1; }
                 for (int i = 0; i < kMaxYGroups * 32; ++i) w.col_off[i] = -1;
@@ -560,7 +560,7 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
             rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
             g_prof.stop(st);
             if (rc) return rc;
-            b.skip_if_le = cap_rows;        // the FFMA kernel below only runs when the list overflowed the images
+            b.skip_if_le = cap_rows;        // the FFMA kernel below only handles what overflowed the images
         }
         if (!use_mma && getenv("T2N_BWD_TRACE")) {
             if (!g_trace) cudaMalloc(&g_trace, kTraceLen * sizeof(long long));

@@ -286,7 +286,8 @@ struct AppBwdArgs {
     const float* act_h1;        // [A][128] saved relu(layer 1) / relu(layer 2) of the forward, or NULL
     const float* act_h2;
     long long act_rows;
-    long long skip_if_le;       // >= 0: do nothing when the list has <= this many samples (the tensor-core path ran)
+    long long skip_if_le;       // >= 0: the tensor-core path handled the first skip_if_le listed samples (a multiple of 128);
+                                // this kernel then processes only the entries beyond them (nothing if the list is shorter)
     long long* trace;           // debug cycle counters of CTA 0 (NULL = off)
 };
 
@@ -368,7 +369,8 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = a.counters[0];
     if (b.skip_if_le >= 0 && (long long)total <= b.skip_if_le) return;
-    if (tid == 0 && blockIdx.x * kTM < total) atomicAdd(const_cast<int32_t*>(a.counters) + 3, 1);   // path marker
+    if (tid == 0 && ((b.skip_if_le > 0 ? b.skip_if_le : 0) + (long long)blockIdx.x * kTM) < total)
+        atomicAdd(const_cast<int32_t*>(a.counters) + 3, 1);   // path marker
     const int C = a.C;
     const int NA = a.n_app_total;
     const bool mlp = a.shading <= T2N_SHADE_MLP;
@@ -400,7 +402,8 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
     for (int i = 0; i < kMaxBasisPerThread; ++i) gB[i] = 0.f;
     float gW3a = 0.f, gW3b = 0.f, gb1 = 0.f, gb2 = 0.f, gb3 = 0.f;
 
-    for (int tile = blockIdx.x; tile * kTM < total; tile += gridDim.x) {
+    const int first_tile = b.skip_if_le > 0 ? (int)(b.skip_if_le / kTM) : 0;
+    for (int tile = first_tile + blockIdx.x; tile * kTM < total; tile += gridDim.x) {
         const int e0 = tile * kTM;
         // ---------------- G: gather products (kept for the basis gradient) + base extras
         ++ntile; mark(11);

@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_addr = smem_u32(sm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = a.counters[0];
-    if (total <= 0 || (long long)total > args.cap_rows) return;
+    // listed samples beyond the images' capacity are left to the recomputing FFMA kernel (AppBwdArgs::skip_if_le)
+    const int listed = a.counters[0];
+    const int total = (long long)listed > args.cap_rows ? (int)args.cap_rows : listed;
+    if (total <= 0) return;
     const int tiles_total = (total + kMmaM - 1) / kMmaM;
     int n_tiles = 0;
     for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) ++n_tiles;

@@ -146,7 +146,9 @@ struct WgradArgs {
     const uint8_t* y_img;
     int ngy;
     const int32_t* counters;    // [0] = number of listed samples
-    long long cap_rows;         // image capacity; total > cap_rows -> the kernel does nothing (fallback path runs)
+    long long cap_rows;         // image capacity (rows, multiple of 128)
+    int clamp;                  // 1: a longer list is processed up to cap_rows (the backward: the rest takes the FFMA kernel);
+                                // 0: a longer list makes the kernel do nothing (t2n_debug_wgrad)
     int n_stages;
     int terms;                  // bit0 hi.hi  bit1 lo.hi  bit2 hi.lo
     float* out;                 // out[row_off[lane] + col_off[col]] += D[lane][col]   (negative offset = skip)

@@ -38,8 +38,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = a.counters[0];
-    if (total <= 0 || (long long)total > a.cap_rows) return;
+    const int listed = a.counters[0];
+    if (listed <= 0 || (!a.clamp && (long long)listed > a.cap_rows)) return;
+    const int total = (long long)listed > a.cap_rows ? (int)a.cap_rows : listed;
     const int tiles_total = (total + 127) >> 7;
     int n_tiles = 0;
     for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) ++n_tiles;
