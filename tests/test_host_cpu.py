@@ -160,3 +160,40 @@ def test_tv_regulariser_matches_oracle():
     ref = sum(orc.tv_plane(c.params[f"density_plane.{i}"]) for i in range(3)) * 1e-2
     got = m.TV_loss_density(orc.tv_plane)
     assert abs(float(got) - float(ref)) <= 1e-6 * abs(float(ref))
+
+
+def test_training_entry_points_validate_arguments_without_gpu():
+    """The fused-loss / TV / Adam entry points refuse bad arguments before touching a device."""
+    lib = nat.load()
+    assert lib.t2n_data_loss(None, 4, 4, None, None, 0.0, 0.0, 0.0, 1.0, None, None, None, None, None, None) == -1
+    assert lib.t2n_tv_plane_sums(None, 4, 4, 4, None, None) == -1
+    assert lib.t2n_tv_plane_grad(None, 4, 4, 4, None, 1.0, 1.0, None, None) == -1
+    assert lib.t2n_adam_step(None, 0, 0.9, 0.99, 1e-8, 0.0, 1, None) == -1
+    t = (nat.T2NAdamTensor * 1)()
+    assert lib.t2n_adam_step(t, 1, 1.5, 0.99, 1e-8, 0.0, 1, None) == -1       # beta1 out of range
+    assert lib.t2n_adam_step(t, 1, 0.9, 0.99, 1e-8, 0.0, 0, None) == -1       # step counts from 1
+    assert C.sizeof(nat.T2NTransGrad) == 8 * 3 and C.sizeof(nat.T2NAdamTensor) == 8 * 6
+
+
+def test_fused_training_paths_refuse_cpu_tensors_and_generic_tv_callables_stay_tensor_ops():
+    from text2nerf_b200.optim import FusedAdam
+    c = Case("t2n_noview_train")
+    m = build_model(c.spec, c.params, "cpu")
+    with pytest.raises(nat.NativeLibraryError):
+        m.data_loss(c.rays, c.rgb_gt, c.depth_gt, N_samples=c.n_samples)
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(nat.NativeLibraryError):
+        FusedAdam([p]).step()
+    with pytest.raises(ValueError):
+        FusedAdam([p], betas=(1.0, 0.99))
+    # TV_loss_* take arbitrary callables (tensoRF.py:193-203): CPU planes / non-TVLoss callables use tensor ops
+    class TVLoss(torch.nn.Module):
+        TVLoss_weight = 1
+
+        def forward(self, x):
+            return orc.tv_plane(x)
+    want = sum(orc.tv_plane(pl) * 1e-2 for pl in m.density_plane)
+    assert torch.equal(m.TV_loss_density(TVLoss()), want)                 # CPU planes: no kernel route
+    assert torch.equal(m.TV_loss_density(orc.tv_plane), want)
+    assert torch.equal(m.TV_loss_app(lambda x: x.abs().mean()), sum(pl.abs().mean() * 1e-2 for pl in m.app_plane))
