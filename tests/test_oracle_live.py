@@ -84,3 +84,42 @@ def test_mlp_pe_is_broken_in_reference_too():
     rays = torch.tensor([[0.0, 0.0, -0.9, 0.0, 0.0, 1.0]])
     with pytest.raises(RuntimeError):
         ref(rays, is_train=True, white_bg=True, ndc_ray=0, N_samples=16)
+
+
+def _ref_utils():
+    """The reference's utils.py (TVLoss :488-504, TransMittanceLoss_mask :67-80) with stub modules for the packages it
+    imports at module level that are absent here and unused by the two classes."""
+    import importlib
+    import types
+    if REFERENCE_DIR not in sys.path:
+        sys.path.insert(0, REFERENCE_DIR)
+    for name in ["imageio", "imageio.v2", "statsmodels", "statsmodels.api", "kornia", "plyfile", "skimage", "skimage.io",
+                 "skimage.measure", "lpips", "configargparse"]:
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    return importlib.import_module("utils")
+
+
+def test_loss_terms_match_the_reference_classes():
+    """oracle.training_loss / oracle.tv_plane -- the formulas the fused CUDA loss, TV and golden gradients are checked
+    against -- equal the reference's own utils.TransMittanceLoss_mask and utils.TVLoss bit for bit."""
+    ru = _ref_utils()
+    g = torch.Generator().manual_seed(9)
+    R, S = 64, 37
+    rgb, rgb_gt = torch.rand(R, 3, generator=g), torch.rand(R, 3, generator=g)
+    depth, depth_gt = 1 + 5 * torch.rand(R, generator=g), 1 + 5 * torch.rand(R, generator=g)
+    z = torch.sort(0.5 + 7 * torch.rand(R, S, generator=g), dim=1).values
+    w = 0.05 * torch.rand(R, S, generator=g)
+    # text2nerf_main.py:563-575 written with the reference's class
+    loss = torch.mean((rgb - rgb_gt) ** 2)
+    depth_loss = torch.mean((depth - depth_gt) ** 2)
+    mask_rays = (z - depth_gt[:, None] + 0.1) < 0
+    trans_loss = ru.TransMittanceLoss_mask("cpu")(w, mask_rays)
+    want = loss + 0.005 * depth_loss + 1e3 * trans_loss
+    assert torch.equal(orc.training_loss(rgb, depth, z, w, rgb_gt, depth_gt), want)
+    x = torch.randn(1, 16, 23, 31, generator=g)
+    for weight in (1, 0.25):
+        assert torch.equal(weight * orc.tv_plane(x), ru.TVLoss(weight)(x))
