@@ -60,14 +60,64 @@ def parse():
     return ap.parse_args()
 
 
-def make_spec():
-    from oracle import t2n_oracle as orc       # spec/param generator only; never on the timed product path
-    return orc.FieldSpec(aabb=AABB, grid=GRID, near_far=NEAR_FAR, step_ratio=STEP_RATIO)
+# ---- the synthetic workload is generated here, by plain tensor code: the product arm never imports oracle/ ----------
+N_SIGMA, N_APP, APP_DIM, FEATURE_C, MLP_IN = [16, 16, 16], [48, 48, 48], 27, 128, 27 + 2 * 6 * 27   # MLP_Fea_noview, fea_pe 6
+MAT_AXES, VEC_AXIS = ((0, 1), (0, 2), (1, 2)), (2, 1, 0)          # models/tensorBase.py:190-191
 
 
-def make_params(spec):
+def make_params(seed=0, density_gain=10.8, app_gain=1.0):
+    """Seeded "fog" field with the reference's state-dict keys and shapes (models/tensoRF.py:144-160, tensorBase.py:94-99):
+    0.1 * randn factors, the density factors scaled so that ~10 % of the box is occupied."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+
+    def randn(*shape):
+        return torch.randn(*shape, generator=g, dtype=torch.float32)
+
+    for i in range(3):
+        (a0, a1), v = MAT_AXES[i], VEC_AXIS[i]
+        p[f"density_plane.{i}"] = 0.1 * density_gain * randn(1, N_SIGMA[i], GRID[a1], GRID[a0])
+        p[f"density_line.{i}"] = 0.1 * density_gain * randn(1, N_SIGMA[i], GRID[v], 1)
+        p[f"app_plane.{i}"] = 0.1 * app_gain * randn(1, N_APP[i], GRID[a1], GRID[a0])
+        p[f"app_line.{i}"] = 0.1 * app_gain * randn(1, N_APP[i], GRID[v], 1)
+    p["basis_mat.weight"] = randn(APP_DIM, sum(N_APP)) / math.sqrt(sum(N_APP))
+    p["renderModule.mlp.0.weight"] = randn(FEATURE_C, MLP_IN) / math.sqrt(MLP_IN)
+    p["renderModule.mlp.0.bias"] = 0.1 * randn(FEATURE_C)
+    p["renderModule.mlp.2.weight"] = randn(FEATURE_C, FEATURE_C) / math.sqrt(FEATURE_C)
+    p["renderModule.mlp.2.bias"] = 0.1 * randn(FEATURE_C)
+    p["renderModule.mlp.4.weight"] = randn(3, FEATURE_C) / math.sqrt(FEATURE_C)
+    p["renderModule.mlp.4.bias"] = torch.zeros(3)
+    return p
+
+
+def composed_loss(rgb_map, depth_map, z_vals, weight, rgb_gt, depth_gt, w_depth=0.005, w_trans=1e3, delta=0.1):
+    """The data terms as the reference's loop composes them from tensor ops (text2nerf_main.py:563-575,
+    utils.TransMittanceLoss_mask utils.py:67-80): the comparison point of the fused TensorBase.data_loss."""
+    l_rgb = torch.mean((rgb_map - rgb_gt) ** 2)
+    l_depth = torch.mean((depth_map - depth_gt) ** 2)
+    mean_w = torch.mean(weight * ((z_vals - depth_gt[:, None] + delta) < 0), dim=1)
+    return l_rgb + w_depth * l_depth + w_trans * torch.mean(mean_w ** 2)
+
+
+class TVLoss(torch.nn.Module):
+    """utils.TVLoss (utils.py:488-504) as text2nerf_main.py:455 instantiates it (`tvreg`)."""
+
+    def __init__(self, TVLoss_weight=1):
+        super().__init__()
+        self.TVLoss_weight = TVLoss_weight
+
+    def forward(self, x):
+        n_h, n_w = x[:, :, 1:, :].numel(), x[:, :, :, 1:].numel()
+        h_tv = torch.pow(x[:, :, 1:, :] - x[:, :, :-1, :], 2).sum()
+        w_tv = torch.pow(x[:, :, :, 1:] - x[:, :, :, :-1], 2).sum()
+        return self.TVLoss_weight * 2 * (h_tv / n_h + w_tv / n_w) / x.shape[0]
+
+
+def oracle_spec():
+    """FieldSpec of the same workload for the CPU legs (the only place bench.py touches oracle/)."""
     from oracle import t2n_oracle as orc
-    return orc.init_params(spec, seed=0, density_gain=10.8, app_gain=1.0)
+    return orc.FieldSpec(aabb=AABB, grid=GRID, near_far=NEAR_FAR, step_ratio=STEP_RATIO)
 
 
 def view_pose(rank):
@@ -79,12 +129,19 @@ def view_pose(rank):
                          [-math.sin(a), 0.0, math.cos(a), 0.0]], dtype=torch.float32)
 
 
-def host_rays(rank):
-    from oracle import t2n_oracle as orc
-    d = orc.pixel_directions(H, W, [FOCAL, FOCAL])
+def pinhole_rays(h, w, focal, c2w):
+    """[h*w, 6] rays of a pin-hole view on the host: pixel centres at +0.5, OpenCV axes, normalised directions
+    (dataLoader/ray_utils.py:24-42, scene_gen.py:45), rotated by the pose without renormalisation (ray_utils.py:66-87)."""
+    ys, xs = torch.meshgrid(torch.linspace(0, h - 1, h), torch.linspace(0, w - 1, w), indexing="ij")
+    d = torch.stack([(xs + 0.5 - w / 2) / focal, (ys + 0.5 - h / 2) / focal, torch.ones_like(xs)], -1)
     d = d / torch.norm(d, dim=-1, keepdim=True)
-    ro, rd = orc.camera_rays(d, view_pose(rank))
-    return torch.cat([ro, rd], -1).contiguous()
+    rd = d @ c2w[:3, :3].T
+    ro = c2w[:3, 3].expand(rd.shape)
+    return torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3)], -1).contiguous()
+
+
+def host_rays(rank):
+    return pinhole_rays(H, W, FOCAL, view_pose(rank))
 
 
 class ClockSampler:
@@ -170,8 +227,8 @@ def run_reference_arm(args, rank):
     ATen ops, tests pin it bit-exact to the unmodified reference) on the box's host cores."""
     if rank != 0:
         return
-    spec = make_spec()
-    params = make_params(spec)
+    spec = oracle_spec()
+    params = make_params()
     rays = host_rays(0)
     n, times = cpu_reference_leg(spec, params, rays, args.steps, max(1, min(args.warmup, 1)), "fwd")
     total = sum(times)
@@ -203,7 +260,6 @@ def main():
     from text2nerf_b200 import OctreeRender_trilinear_fast, TensorVMSplit, _native as nat
     from text2nerf_b200 import dist as t2n_dist
     from text2nerf_b200 import ray_utils
-    from oracle import t2n_oracle as orc      # only: synthetic spec/params, the loss formula, cpu_baseline
 
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
     dev = torch.device("cuda", local_rank)
@@ -212,19 +268,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     nat.load()
 
-    spec = make_spec()
-    params = make_params(spec)
-    S = orc.derive_step(spec)[1]
+    params = make_params()
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
-        model = TensorVMSplit(spec.aabb_t().to(dev), GRID, dev, density_n_comp=[16, 16, 16],
+        model = TensorVMSplit(torch.tensor(AABB, dtype=torch.float32, device=dev), GRID, dev, density_n_comp=[16, 16, 16],
                               appearance_n_comp=[48, 48, 48], app_dim=27, near_far=NEAR_FAR,
                               shadingMode="MLP_Fea_noview", alphaMask_thres=0.001, density_shift=-10,
                               distance_scale=25, pos_pe=6, view_pe=2, fea_pe=6, featureC=128,
                               step_ratio=STEP_RATIO, fea2denseAct="softplus")
     model.load_state_dict({k: v.to(dev) for k, v in params.items()})
-    assert model.nSamples == S == 1036
+    S = model.nSamples
+    assert S == 1036
 
     pose = view_pose(rank)
     rays_dev = ray_utils.camera_rays(pose, H, W, [FOCAL, FOCAL], normalize=True, device=dev)
@@ -340,7 +395,7 @@ def main():
             for rays_b, rgb_gt, depth_gt in batches:
                 flat.zero_()
                 out = model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S)
-                orc.training_loss(*out, rgb_gt, depth_gt).backward()
+                composed_loss(*out, rgb_gt, depth_gt).backward()
                 t2n_dist.allreduce_flat_grads(model, world)
 
         for _ in range(max(args.warmup, 3)):
@@ -369,12 +424,6 @@ def main():
         # (TV_weight_density 0.1, TV_weight_app 0.01, configs/text2nerf_scenes.txt:31-32), fused against composed
         from text2nerf_b200.optim import FusedAdam
 
-        class TVLoss(torch.nn.Module):          # the reference's utils.TVLoss (utils.py:488-504) as the loop passes it
-            TVLoss_weight = 1
-
-            def forward(self, x):
-                return self.TVLoss_weight * orc.tv_plane(x)
-
         tvreg = TVLoss()
 
         def make_iteration(fused):
@@ -387,8 +436,8 @@ def main():
                     if fused:
                         total = model.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S)
                     else:
-                        total = orc.training_loss(*model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S),
-                                                  rgb_gt, depth_gt)
+                        total = composed_loss(*model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S),
+                                              rgb_gt, depth_gt)
                     total = total + model.TV_loss_density(reg) * 0.1 + model.TV_loss_app(reg) * 0.01
                     total.backward()
                     t2n_dist.allreduce_flat_grads(model, world)
@@ -416,6 +465,7 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        spec = oracle_spec()
         n, times = cpu_reference_leg(spec, params, rays_pinned, 2, 1, "fwd")
         cpu = {"value": n / min(times) / 1e6, "unit": "Mrays/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{n} random rays of the same 800x800 view, S=1036, eval forward, best of 2 after 1 warm-up"}

@@ -21,17 +21,15 @@ def main():
     ap.add_argument("--train-batches", type=int, default=1)
     ap.add_argument("--batch", type=int, default=bench.TRAIN_BATCH)
     a = ap.parse_args()
-    from oracle import t2n_oracle as orc
     from text2nerf_b200 import TensorVMSplit, ray_utils
     dev = torch.device("cuda:0")
-    spec = bench.make_spec()
-    params = bench.make_params(spec)
-    S = orc.derive_step(spec)[1]
+    params = bench.make_params()
     with contextlib.redirect_stdout(io.StringIO()):
-        model = TensorVMSplit(spec.aabb_t().to(dev), bench.GRID, dev, density_n_comp=[16, 16, 16],
+        model = TensorVMSplit(torch.tensor(bench.AABB, dtype=torch.float32, device=dev), bench.GRID, dev, density_n_comp=[16, 16, 16],
                               appearance_n_comp=[48, 48, 48], app_dim=27, near_far=bench.NEAR_FAR,
                               shadingMode="MLP_Fea_noview", step_ratio=bench.STEP_RATIO, fea_pe=6, view_pe=2)
     model.load_state_dict({k: v.to(dev) for k, v in params.items()})
+    S = model.nSamples
     rays = ray_utils.camera_rays(bench.view_pose(0), bench.H, bench.W, [bench.FOCAL] * 2, device=dev)[:a.rays].contiguous()
     for _ in range(a.views):
         with torch.no_grad():

@@ -8,18 +8,17 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
-from oracle import t2n_oracle as orc
 from text2nerf_b200 import TensorVMSplit, ray_utils
 
 dev = torch.device("cuda:0")
 peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 
-def build(spec, params):
+def build(aabb, near_far, step_ratio, params):
     with contextlib.redirect_stdout(io.StringIO()):
-        m = TensorVMSplit(spec.aabb_t().to(dev), list(spec.grid), dev, density_n_comp=[16, 16, 16], appearance_n_comp=[48, 48, 48],
-                          app_dim=27, near_far=list(spec.near_far), shadingMode="MLP_Fea_noview", step_ratio=spec.step_ratio,
-                          fea_pe=6, view_pe=2)
+        m = TensorVMSplit(torch.tensor(aabb, dtype=torch.float32, device=dev), bench.GRID, dev, density_n_comp=[16, 16, 16],
+                          appearance_n_comp=[48, 48, 48], app_dim=27, near_far=near_far, shadingMode="MLP_Fea_noview",
+                          step_ratio=step_ratio, fea_pe=6, view_pe=2)
     m.load_state_dict({k: v.to(dev) for k, v in params.items()})
     return m
 
@@ -61,9 +60,8 @@ def measure(model, rays, S, reps):
 
 out = {"peak_GBps": peak}
 # (a) sweep at the bench field
-spec = bench.make_spec()
-model = build(spec, bench.make_params(spec))
-S = orc.derive_step(spec)[1]
+model = build(bench.AABB, bench.NEAR_FAR, bench.STEP_RATIO, bench.make_params())
+S = model.nSamples
 full = ray_utils.camera_rays(bench.view_pose(0), bench.H, bench.W, [bench.FOCAL] * 2, normalize=True, device=dev)
 g = torch.Generator().manual_seed(0)
 out["sweep_lego_300"] = []
@@ -75,14 +73,10 @@ for e in range(10, 21):
 del model
 torch.cuda.empty_cache()
 # (b) T2N training shape: box +-8, step_ratio 1.0 (S = 259 as text2nerf_main.py halves nSamples), camera near the origin
-spec2 = orc.FieldSpec(aabb=[[-8, -8, -8], [8, 8, 8]], grid=[300, 300, 300], near_far=[0.5, 8.0], step_ratio=1.0)
-model2 = build(spec2, orc.init_params(spec2, seed=0, density_gain=10.8, app_gain=1.0))
-d = orc.pixel_directions(512, 512, [512.0, 512.0])
-d = d / torch.norm(d, dim=-1, keepdim=True)
+model2 = build([[-8, -8, -8], [8, 8, 8]], [0.5, 8.0], 1.0, bench.make_params())
 pose = torch.tensor([[1.0, 0, 0, 0.1], [0, 1.0, 0, -0.05], [0, 0, 1.0, 0.2]])
-ro, rd = orc.camera_rays(d, pose)
-rays2 = torch.cat([ro, rd], -1).to(dev)
+rays2 = bench.pinhole_rays(512, 512, 512.0, pose).to(dev)
 idx = torch.randint(0, rays2.shape[0], (16384,), generator=g).to(dev)
-out["t2n_train_shape"] = measure(model2, rays2[idx].contiguous(), orc.derive_step(spec2)[1] // 2, 10)
-out["t2n_view_512"] = measure(model2, rays2.contiguous(), orc.derive_step(spec2)[1] // 2, 3)
+out["t2n_train_shape"] = measure(model2, rays2[idx].contiguous(), model2.nSamples // 2, 10)
+out["t2n_view_512"] = measure(model2, rays2.contiguous(), model2.nSamples // 2, 3)
 print(json.dumps(out))

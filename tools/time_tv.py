@@ -6,20 +6,19 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
-from oracle import t2n_oracle as orc
 from text2nerf_b200 import TensorVMSplit
 
 dev = torch.device("cuda:0")
-spec = bench.make_spec()
 with contextlib.redirect_stdout(io.StringIO()):
-    model = TensorVMSplit(spec.aabb_t().to(dev), bench.GRID, dev, density_n_comp=[16, 16, 16], appearance_n_comp=[48, 48, 48],
+    model = TensorVMSplit(torch.tensor(bench.AABB, dtype=torch.float32, device=dev), bench.GRID, dev, density_n_comp=[16, 16, 16], appearance_n_comp=[48, 48, 48],
                           app_dim=27, near_far=bench.NEAR_FAR, shadingMode="MLP_Fea_noview", step_ratio=bench.STEP_RATIO)
 flat = model.enable_flat_grads(True)
+tvreg = bench.TVLoss().forward        # a plain callable: the tensor-op route (the TVLoss module itself takes the fused kernels)
 
 
 def step():
     flat.zero_()
-    loss = model.TV_loss_density(orc.tv_plane) * 0.1 + model.TV_loss_app(orc.tv_plane) * 0.01
+    loss = model.TV_loss_density(tvreg) * 0.1 + model.TV_loss_app(tvreg) * 0.01
     loss.backward()
 
 

@@ -12,15 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["T2N_BWD_TRACE"] = "1"
 import bench  # noqa: E402
-from oracle import t2n_oracle as orc  # noqa: E402
 from text2nerf_b200 import TensorVMSplit, _native as nat, ray_utils  # noqa: E402
 
 dev = torch.device("cuda:0")
-spec = bench.make_spec()
-params = bench.make_params(spec)
-S = orc.derive_step(spec)[1]
+params = bench.make_params()
 with contextlib.redirect_stdout(io.StringIO()):
-    model = TensorVMSplit(spec.aabb_t().to(dev), bench.GRID, dev, density_n_comp=[16, 16, 16], appearance_n_comp=[48, 48, 48],
+    model = TensorVMSplit(torch.tensor(bench.AABB, dtype=torch.float32, device=dev), bench.GRID, dev, density_n_comp=[16, 16, 16], appearance_n_comp=[48, 48, 48],
                           app_dim=27, near_far=bench.NEAR_FAR, shadingMode="MLP_Fea_noview", step_ratio=bench.STEP_RATIO,
                           fea_pe=6, view_pe=2)
 model.load_state_dict({k: v.to(dev) for k, v in params.items()})
@@ -29,7 +26,7 @@ g = torch.Generator().manual_seed(0)
 for _ in range(2):
     idx = torch.randint(0, rays.shape[0], (4096,), generator=g).to(dev)
     out = model(rays[idx].contiguous(), is_train=True, white_bg=True, N_samples=S)
-    orc.training_loss(*out, torch.rand(4096, 3, generator=g).to(dev), (2 + 4 * torch.rand(4096, generator=g)).to(dev)).backward()
+    bench.composed_loss(*out, torch.rand(4096, 3, generator=g).to(dev), (2 + 4 * torch.rand(4096, generator=g)).to(dev)).backward()
 torch.cuda.synchronize()
 buf = (C.c_longlong * 32)()
 nat.load().t2n_debug_trace_read(buf)
