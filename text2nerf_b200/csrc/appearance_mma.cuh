@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_forward_mma_kernel(const _
                 for (int q = 0; q < 8; ++q) {
                     const int e = (q < 4) ? (4 * eq + q) : (16 + 4 * eq + (q - 4));
                     sn[q] = 0.f; cs[q] = 1.f;
-                    if (args.pe_nf[e] > 0) sincosf(brow[args.pe_src[e]], &sn[q], &cs[q]);
+                    if (args.pe_nf[e] > 0) sincos_pe(brow[args.pe_src[e]], &sn[q], &cs[q]);
                 }
             }
             tmark(kStepS1, ts0);

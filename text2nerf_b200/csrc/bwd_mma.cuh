@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 sn[i] = 0.f; cs[i] = 1.f;
-                if (nf[i] > 0) sincosf(bv[i], &sn[i], &cs[i]);
+                if (nf[i] > 0) sincos_pe(bv[i], &sn[i], &cs[i]);
             }
             float scale = 1.f;
             for (int f = 0; f < args.n_freq; ++f) {

@@ -107,6 +107,25 @@ __device__ __forceinline__ Axis make_axis(int i0, float fr, int size) {
     return ax;
 }
 
+// sin and cos of the frequency-0 angle of a positional-encoding entry.  Appearance features are mostly small: inside
+// [-pi/4, pi/4] the minimax polynomials of the library's own fast path (< 1 ulp) are evaluated directly, without the
+// range reduction, quadrant logic and slow-path test of sincosf (~20 instead of ~45 instructions on a serial chain that
+// every producer thread runs 8 times per tile); anything larger takes sincosf.
+__device__ __forceinline__ void sincos_pe(float x, float* sn, float* cs) {
+    if (fabsf(x) <= 0.78539816f) {
+        const float s = x * x;
+        float ps = fmaf(-1.95152959e-4f, s, 8.33216087e-3f);
+        ps = fmaf(ps, s, -1.66666546e-1f);
+        *sn = fmaf(ps * s, x, x);
+        float pc = fmaf(2.44331571e-5f, s, -1.38873163e-3f);
+        pc = fmaf(pc, s, 4.16666457e-2f);
+        pc = fmaf(pc, s, -0.5f);
+        *cs = fmaf(pc, s, 1.0f);
+    } else {
+        sincosf(x, sn, cs);
+    }
+}
+
 __device__ __forceinline__ float softplus_t(float x) {           // F.softplus beta=1 threshold=20
     return x > 20.f ? x : log1pf(expf(x));
 }

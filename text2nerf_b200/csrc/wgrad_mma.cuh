@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_mma_kernel(const __gri
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     sn[i] = 0.f; cs[i] = 1.f;
-                    if (nf[i] > 0) sincosf(bv[i], &sn[i], &cs[i]);
+                    if (nf[i] > 0) sincos_pe(bv[i], &sn[i], &cs[i]);
                 }
                 if (it >= (uint32_t)NS) mbar_wait(bar_empty + s, ((it / NS) - 1) & 1);
                 uint8_t* yrow = sm + (size_t)s * stage_bytes + xb + r * 128;       // row r of group 0, hi half
