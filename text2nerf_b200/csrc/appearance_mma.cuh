@@ -1,10 +1,12 @@
 // K2, tensor-core variant: the appearance path with every contraction (basis 144->27, decoder
 // 352->128->128) on the 5th-generation tensor cores (tcgen05.mma, kind::tf32, accumulators in
 // TMEM), at fp32-equivalent accuracy through a 3xTF32 split:
-//      x = hi + lo (hi = cvt.rna.tf32(x), lo = x - hi exactly);   A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo
-// (the dropped lo.lo term is 2^-22 relative).  The north-star RGB gate (1e-4) rules out plain
-// TF32/BF16 (SURVEY.md section 7 "Hard parts"); the split costs 3 MMAs per K step and still leaves the
-// tensor pipe far from saturated -- the producers (gathers, sin/cos) are the bound.
+//      x = hi + lo (hi = the TF32 part of x, lo = x - hi exactly);   A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo
+// Weights are split with round-to-nearest when they are packed (once per call); A-operand elements, produced on the fly,
+// by truncation (two instructions instead of five, operand_image.cuh): the dropped lo.lo term and the truncated low
+// bits of lo are ~2^-21 relative.  The north-star RGB gate (1e-4) rules out plain TF32/BF16 (SURVEY.md section 7 "Hard
+// parts"); the split costs 3 MMAs per K step and still leaves the tensor pipe at 44 % -- the producers (gather,
+// decoder columns, chunk hand-offs) are the bound (profiles/r1r_forward_and_training.md).
 //
 // One persistent CTA per SM walks the compacted app-sample list in tiles of 128 entries (= UMMA M).
 // Operands are K-major chunks of 32 fp32 columns:
