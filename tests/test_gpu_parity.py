@@ -241,3 +241,24 @@ def test_renderer_drop_in_and_rng_contract(cuda_device):
     ref = orc.render_chunked(c.spec, c.params, rays, chunk=32, n_samples=c.n_samples, is_train=True, white_bg=True,
                              jitter=jit)
     _check_forward((rgb, depth, z, w), dict(rgb_map=ref[0], depth_map=ref[2], z_vals=ref[4], weight=ref[3]))
+
+
+def test_eval_render_is_independent_of_the_callers_chunk_size(cuda_device):
+    """Evaluation renders merge the caller's chunks into large launches (renderer.py mirror); the 5-tuple must be what
+    chunk-by-chunk rendering gives, bit for bit, and consume no random numbers."""
+    from text2nerf_b200 import OctreeRender_trilinear_fast
+    c = Case("t2n_noview_eval")
+    model = build_model(c.spec, c.params, cuda_device)
+    rays = c.rays.to(cuda_device)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        merged = OctreeRender_trilinear_fast(rays, model, chunk=16, N_samples=c.n_samples, white_bg=True, is_train=False,
+                                             device=cuda_device)
+        after = torch.rand(1)
+        torch.manual_seed(5)
+        assert torch.equal(after, torch.rand(1))            # the render left the CPU generator untouched
+        pieces = [model(rays[s:s + 16], is_train=False, white_bg=True, N_samples=c.n_samples) for s in range(0, rays.shape[0], 16)]
+    want = [torch.cat([p[i] for p in pieces]) for i in range(4)]       # rgb, depth, z_vals, weight
+    assert merged[1] is None
+    for got, ref in zip((merged[0], merged[2], merged[4], merged[3]), want):
+        assert torch.equal(got, ref)

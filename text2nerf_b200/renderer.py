@@ -29,6 +29,12 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
                                 is_train=False, device='cuda'):
     n_rays = rays.shape[0]
     parts = ([], [], [], [])
+    if not is_train and white_bg:
+        # Evaluation renders draw no random numbers (no jitter, tensorBase.py:313-317; no background draw when white_bg,
+        # :497) and rays are independent, so chunk boundaries cannot change any output: callers' small chunks (4096 /
+        # 8192 in renderer.evaluation*) are merged into launches that fill the GPU (the kernels reach full throughput
+        # from ~65 k rays).  Training calls keep the caller's chunks: each draws torch.rand(R, 1) from the CPU generator.
+        chunk = max(int(chunk), 1 << 18)
     for start in range(0, n_rays, chunk):
         rays_chunk = rays[start:start + chunk].to(device, non_blocking=True)
         out = tensorf(rays_chunk, is_train=is_train, white_bg=white_bg, ndc_ray=ndc_ray, N_samples=N_samples)
