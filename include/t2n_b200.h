@@ -302,6 +302,11 @@ int t2n_profile_enable(int on);
 /* Debug aid: with T2N_MMA_TRACE set in the environment the tensor-core appearance kernel's CTA 0 writes
  * 32 cycle counters (stage times, barrier waits); this copies them to the host.  Returns 32 or 0. */
 int t2n_debug_trace_read(long long* out32);
+/* Test aid (host only, no device needed): the chunk program the tensor-core appearance kernel's producer, issuer and
+ * loader roles walk (csrc/appearance_mma_defs.cuh build_program) for sum(n_app) product channels and Kp padded decoder
+ * columns.  One byte per step, kind = byte & 7 (0 S2 chunk, 1 S1 chunk, 2 gather unit, 3 Pre, 4 Ray, 5 Pro, 6 S3),
+ * index = byte >> 3.  Returns the number of steps (<= cap, cap >= 80) or a negative error code. */
+int t2n_debug_chunk_program(int n_app_total, int Kp, unsigned char* out, int cap);
 /* Same, first n entries of the trace buffer (counters + the per-chunk timeline events of three iterations). */
 int t2n_debug_trace_read_n(long long* out, int n);
 int t2n_profile_read(int* ids, float* ms, int n);

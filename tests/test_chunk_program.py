@@ -1,0 +1,116 @@
+"""Host-side model check of the chunk program of the tensor-core appearance kernel (csrc/appearance_mma_defs.cuh
+build_program, exported as t2n_debug_chunk_program): the table the producer, issuer and loader roles walk, and the
+mbarrier protocol the producers run on top of it (csrc/appearance_mma.cuh), for every decoder shape inside the
+tensor-core envelope -- the GPU tests exercise only a handful of shapes.
+
+Invariants checked by simulating the producers' bookkeeping (it, n0, done_known, s0_last) exactly as the kernel keeps it:
+  * structure: all S2 chunks precede S1 chunk 0, which precedes Pro and every gather unit; S1 chunks and units appear in
+    order; unit 2c+1 (which publishes basis chunk c) follows unit 2c;
+  * every wait targets a chunk this warp has already published (no self-deadlock) and lies inside the 4-slot window of
+    the chunk-done ring (p >= it - 4: the slot's phase cannot have been reused);
+  * when a chunk is published, chunk it - 4 is known complete (the a_full slot is free);
+  * the TMEM A stage (it % 3) and the shared-memory A stage (n0 & 1) written for a chunk were last used by a chunk that
+    is known complete."""
+import ctypes as C
+import itertools
+
+import pytest
+
+from text2nerf_b200 import _native as nat
+
+S2, S1, U, PRE, RAY, PRO, S3 = range(7)
+
+
+def program(n_app_total, Kp):
+    buf = (C.c_ubyte * 80)()
+    n = nat.load().t2n_debug_chunk_program(n_app_total, Kp, buf, 80)
+    assert n > 0, (n_app_total, Kp, n)
+    return [(b & 7, b >> 3) for b in buf[:n]]
+
+
+def shapes():
+    for n_app_total in range(16, 161, 16):
+        for pc, F in itertools.product((1, 2), range(0, 11)):
+            if F == 0 and pc == 2:
+                continue
+            yield n_app_total, 32 * (1 + F * pc)
+
+
+@pytest.mark.parametrize("n_app_total,Kp", list(shapes()))
+def test_program_structure(n_app_total, Kp):
+    prog = program(n_app_total, Kp)
+    nk0, nk1, nk2 = (n_app_total + 31) // 32, Kp // 32, 4
+    kinds = [k for k, _ in prog]
+    assert kinds[0] == PRE and kinds[-1] == S3 and kinds.count(PRO) == 1 and kinds.count(RAY) == 1
+    assert [i for k, i in prog if k == S2] == list(range(nk2))
+    assert [i for k, i in prog if k == S1] == list(range(nk1))
+    assert [i for k, i in prog if k == U] == list(range(2 * nk0))
+    pos = {step: n for n, step in enumerate(prog)}
+    assert max(pos[(S2, c)] for c in range(nk2)) < pos[(S1, 0)] < pos[(PRO, 0)] < pos[(U, 0)]
+    assert pos[(RAY, 0)] < pos[(PRO, 0)] and pos[(PRE, 0)] < pos[(RAY, 0)]
+    # the producers' straight-line head is Pre, S2 [0, early), Ray, S2 [early, nk2), S1 chunk 0, Pro
+    assert prog[:nk2 + 4] == [(PRE, 0), (S2, 0), (S2, 1), (RAY, 0), (S2, 2), (S2, 3), (S1, 0), (PRO, 0)]
+    assert len(prog) <= 80
+
+
+def simulate(prog, n_tiles):
+    it, n0, done_known, s0_last = 0, 0, -1, [-1, -1]
+    published = []                      # (kind, tile, idx) in publish order
+    last_ts_stage_user = {}
+
+    def wait_done(p):
+        nonlocal done_known
+        if p > done_known:
+            assert 0 <= p < it, "waits on a chunk this warp has not published"
+            assert p >= it - 4, "chunk-done slot window exceeded"
+            done_known = p
+
+    for j in range(n_tiles + 2):
+        ok = {S2: 2 <= j < n_tiles + 2, S1: 1 <= j < n_tiles + 1, U: j < n_tiles}
+        for kind, idx in prog:
+            if kind in (PRE, RAY, PRO, S3) or not ok[kind]:
+                continue
+            if kind in (S1, S2):
+                wait_done(it - 3)
+                stage = it % 3
+                assert last_ts_stage_user.get(stage, -1) <= done_known, "TMEM A stage still in use"
+                last_ts_stage_user[stage] = it
+                assert it - 4 <= done_known, "a_full slot of chunk it-4 not free"
+                published.append((kind, j - (2 if kind == S2 else 1), idx))
+                it += 1
+            else:
+                st = n0 & 1
+                if idx % 2 == 0:
+                    wait_done(s0_last[st])
+                    assert s0_last[st] <= done_known, "shared-memory A stage still in use"
+                else:
+                    wait_done(it - 4)
+                    assert it - 4 <= done_known
+                    s0_last[st] = it
+                    n0 += 1
+                    published.append((U, j, idx // 2))
+                    it += 1
+    return published
+
+
+def roles_order(prog, n_tiles):
+    """Chunk order as the issuer / loader derive it from the same table (is_chunk && step_ok)."""
+    out = []
+    for j in range(n_tiles + 2):
+        for kind, idx in prog:
+            if kind > U or (kind == U and idx % 2 == 0):
+                continue
+            t = j - (2 if kind == S2 else 1 if kind == S1 else 0)
+            if 0 <= t < n_tiles:
+                out.append((kind, t, idx // 2 if kind == U else idx))
+    return out
+
+
+@pytest.mark.parametrize("n_tiles", [1, 2, 3, 5])
+def test_protocol_invariants_for_every_shape(n_tiles):
+    for n_app_total, Kp in shapes():
+        prog = program(n_app_total, Kp)
+        published = simulate(prog, n_tiles)
+        assert published == roles_order(prog, n_tiles), (n_app_total, Kp)
+        nk0, nk1 = (n_app_total + 31) // 32, Kp // 32
+        assert len(published) == n_tiles * (nk0 + nk1 + 4)

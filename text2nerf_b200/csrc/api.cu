@@ -364,6 +364,13 @@ int t2n_data_loss(const T2NOutputs* out, int R, int S, const float* rgb_gt, cons
     return rc;
 }
 
+int t2n_debug_chunk_program(int n_app_total, int Kp, unsigned char* out, int cap) {
+    if (!out || n_app_total <= 0 || Kp < 32 || (Kp & 31) || cap < kMaxProg) return T2N_E_BADARG;
+    const MmaPack P = mma_pack_layout(n_app_total, Kp);
+    if (P.basis_chunks > 5 || P.w1_chunks > 1 + 2 * kMaxFreq) return T2N_E_BADARG;
+    return build_program(out, P.basis_chunks, P.w1_chunks, P.w2_chunks);
+}
+
 int t2n_adam_step(const T2NAdamTensor* tensors, int n_tensors, float beta1, float beta2, float eps, float weight_decay,
                   int step, t2n_stream_t stream) {
     if (!tensors || n_tensors < 0 || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f))

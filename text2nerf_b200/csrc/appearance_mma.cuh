@@ -88,40 +88,6 @@ static __global__ void pack_mma_weights_kernel(const float* __restrict__ basis, 
     *reinterpret_cast<float4*>(dst_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-// ---- the chunk program -----------------------------------------------------------------------------------------------
-// Steps of one pipeline iteration, in producer order.  kind in the low 3 bits, index in the high 5.
-//   Pre  (tile j)   load the list slot of this thread's sample
-//   S2 c (tile j-2) layer-2 A chunk c
-//   Ray  (tile j)   load z and the ray of the slot
-//   S1 c (tile j-1) layer-1 A chunk c (c = 0 also moves the feature D0 -> shared memory and seeds sin/cos)
-//   Pro  (tile j)   sample geometry, base vector tail, loads of gather unit 0
-//   U k  (tile j)   gather unit k (16 product channels): consume the prefetched taps, prefetch unit k+1, write half a
-//                   basis A chunk; odd k publishes chunk k/2
-//   S3   (tile j-2) layer 3 + sigmoid
-// Only S2 / S1 / odd-U steps are chunks (B copy, MMAs); the issuer and the loader skip the rest.
-enum : int { kStepS2 = 0, kStepS1 = 1, kStepU = 2, kStepPre = 3, kStepRay = 4, kStepPro = 5, kStepS3 = 6 };
-__device__ inline int build_program(uint8_t* prog, int nk0, int nk1, int nk2) {
-    int n = 0;
-    auto put = [&](int kind, int idx) { prog[n++] = (uint8_t)(kind | (idx << 3)); };
-    put(kStepPre, 0);
-    const int early = nk2 < 2 ? nk2 : 2;
-    for (int c = 0; c < early; ++c) put(kStepS2, c);
-    put(kStepRay, 0);
-    for (int c = early; c < nk2; ++c) put(kStepS2, c);
-    put(kStepS1, 0);
-    put(kStepPro, 0);
-    const int T = nk1 - 1, Un = 2 * nk0;
-    int ts = 0;
-    for (int k = 0; k < Un; ++k) {
-        const int target = ((k + 1) * T + Un - 1) / Un;
-        while (ts < target) { put(kStepS1, 1 + ts); ++ts; }
-        put(kStepU, k);
-    }
-    while (ts < T) { put(kStepS1, 1 + ts); ++ts; }
-    put(kStepS3, 0);
-    return n;
-}
-
 // stage offsets as arithmetic (indexing MmaSmem::a / ::b with a runtime index would put the struct in local memory)
 __device__ __forceinline__ uint32_t a_stage_off(uint32_t i) { return i * (uint32_t)kStageA; }
 __device__ __forceinline__ uint32_t b_stage_off(uint32_t i) { return 2u * (uint32_t)kStageA + i * (uint32_t)kStageB; }

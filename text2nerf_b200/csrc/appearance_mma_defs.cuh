@@ -87,6 +87,43 @@ inline bool build_mma_recipe(int shading, int app_dim, int fea_pe, int view_pe, 
 }
 
 constexpr int kMaxProg = 80;
+
+// ---- the chunk program -----------------------------------------------------------------------------------------------
+// Steps of one pipeline iteration, in producer order.  kind in the low 3 bits, index in the high 5.
+//   Pre  (tile j)   load the list slot of this thread's sample
+//   S2 c (tile j-2) layer-2 A chunk c
+//   Ray  (tile j)   load z and the ray of the slot
+//   S1 c (tile j-1) layer-1 A chunk c (c = 0 also moves the feature D0 -> shared memory and seeds sin/cos)
+//   Pro  (tile j)   sample geometry, base vector tail, loads of gather unit 0
+//   U k  (tile j)   gather unit k (16 product channels): consume the prefetched taps, prefetch unit k+1, write half a
+//                   basis A chunk; odd k publishes chunk k/2
+//   S3   (tile j-2) layer 3 + sigmoid
+// Only S2 / S1 / odd-U steps are chunks (B copy, MMAs); the issuer and the loader skip the rest.
+enum : int { kStepS2 = 0, kStepS1 = 1, kStepU = 2, kStepPre = 3, kStepRay = 4, kStepPro = 5, kStepS3 = 6 };
+__host__ __device__ inline int build_program(uint8_t* prog, int nk0, int nk1, int nk2) {
+    int n = 0;
+#define T2N_PUT(kind, idx) prog[n++] = (uint8_t)((kind) | ((idx) << 3))
+    T2N_PUT(kStepPre, 0);
+    const int early = nk2 < 2 ? nk2 : 2;
+    for (int c = 0; c < early; ++c) T2N_PUT(kStepS2, c);
+    T2N_PUT(kStepRay, 0);
+    for (int c = early; c < nk2; ++c) T2N_PUT(kStepS2, c);
+    T2N_PUT(kStepS1, 0);
+    T2N_PUT(kStepPro, 0);
+    const int T = nk1 - 1, Un = 2 * nk0;
+    int ts = 0;
+    for (int k = 0; k < Un; ++k) {
+        const int target = ((k + 1) * T + Un - 1) / Un;
+        while (ts < target) { T2N_PUT(kStepS1, 1 + ts); ++ts; }
+        T2N_PUT(kStepU, k);
+    }
+    while (ts < T) { T2N_PUT(kStepS1, 1 + ts); ++ts; }
+    T2N_PUT(kStepS3, 0);
+#undef T2N_PUT
+    return n;
+}
+
+
 constexpr int kNB = 4;  // B ring depth: a 32 KB weight chunk needs ~2 MMA-chunk times to arrive from L2
 struct MmaSmem {        // byte offsets from the 1024-aligned base
     int a[2];           // A stages: hi at +0, lo at +kTileBytes
