@@ -49,3 +49,15 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["vs_baseline"] is None
+
+
+def test_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: bench.py's own arm stops with a clear message when there is no CUDA device."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode != 0
+    assert "no CPU fallback" in out.stderr and out.stdout.strip() == ""
