@@ -307,6 +307,11 @@ int t2n_debug_trace_read(long long* out32);
  * columns.  One byte per step, kind = byte & 7 (0 S2 chunk, 1 S1 chunk, 2 gather unit, 3 Pre, 4 Ray, 5 Pro, 6 S3),
  * index = byte >> 3.  Returns the number of steps (<= cap, cap >= 80) or a negative error code. */
 int t2n_debug_chunk_program(int n_app_total, int Kp, unsigned char* out, int cap);
+/* Test aid (host only): the decoder-column recipe of the tensor-core path (csrc/appearance_mma_defs.cuh
+ * build_mma_recipe) for a shading head: out = [n_freq, pe_chunks, Kp, ident_src[32], pe_src[32], pe_nf[32], perm[Kp]]
+ * (perm[k] = column of the reference's mlp[0].weight that internal column k multiplies, -1 = zero weight).  Returns
+ * the number of ints written, or a negative error code if the head is outside the tensor-core envelope. */
+int t2n_debug_mma_recipe(int shading, int app_dim, int fea_pe, int view_pe, int* out, int cap);
 /* Same, first n entries of the trace buffer (counters + the per-chunk timeline events of three iterations). */
 int t2n_debug_trace_read_n(long long* out, int n);
 int t2n_profile_read(int* ids, float* ms, int n);

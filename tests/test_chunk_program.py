@@ -114,3 +114,68 @@ def test_protocol_invariants_for_every_shape(n_tiles):
         assert published == roles_order(prog, n_tiles), (n_app_total, Kp)
         nk0, nk1 = (n_app_total + 31) // 32, Kp // 32
         assert len(published) == n_tiles * (nk0 + nk1 + 4)
+
+
+# ---- decoder-column recipe of the tensor-core path ----------------------------------------------------------------
+import torch  # noqa: E402
+
+from oracle import t2n_oracle as orc  # noqa: E402
+
+HEADS = {"MLP_Fea_noview": 0, "MLP_Fea": 1, "MLP": 2}
+
+
+def mma_recipe(mode, app_dim, fea_pe, view_pe):
+    buf = (C.c_int * 1024)()
+    n = nat.load().t2n_debug_mma_recipe(HEADS[mode], app_dim, fea_pe, view_pe, buf, 1024)
+    if n < 0:
+        return None
+    v = list(buf[:n])
+    return dict(n_freq=v[0], pe_chunks=v[1], Kp=v[2], ident_src=v[3:35], pe_src=v[35:67], pe_nf=v[67:99], perm=v[99:99 + v[2]])
+
+
+@pytest.mark.parametrize("mode,app_dim,fea_pe,view_pe", [
+    ("MLP_Fea_noview", 27, 6, 2), ("MLP_Fea_noview", 27, 0, 0), ("MLP_Fea_noview", 27, 10, 0), ("MLP_Fea_noview", 12, 3, 0),
+    ("MLP_Fea", 27, 2, 2), ("MLP_Fea", 27, 6, 4), ("MLP_Fea", 13, 5, 1), ("MLP_Fea", 27, 3, 0), ("MLP_Fea", 27, 0, 3),
+    ("MLP", 27, 6, 6), ("MLP", 27, 0, 4), ("MLP", 27, 0, 0), ("MLP", 29, 0, 10)])
+def test_mma_recipe_produces_every_reference_column_once(mode, app_dim, fea_pe, view_pe):
+    """Columns generated the way app_forward_mma_kernel generates them (chunk 0 = identity columns, chunk 1 + f*pc + h =
+    (sin, cos)(base[pe_src[16h + e]] * 2^f)) and sent through `perm` reproduce the reference's decoder input
+    (tensorBase.py:62-109, 137-159 via oracle.freq_encode) column for column; everything else has zero weight."""
+    R = mma_recipe(mode, app_dim, fea_pe, view_pe)
+    assert R is not None
+    A = app_dim
+    g = torch.Generator().manual_seed(1)
+    feat, view, xn = torch.randn(4, A, generator=g), torch.randn(4, 3, generator=g), torch.randn(4, 3, generator=g)
+    base = torch.cat([feat, view, xn, torch.zeros(4, 1)], -1).double()
+    assert R["Kp"] == 32 * (1 + R["n_freq"] * R["pe_chunks"]) and len(R["perm"]) == R["Kp"]
+    internal = torch.zeros(4, R["Kp"], dtype=torch.float64)
+    for k in range(32):
+        internal[:, k] = base[:, R["ident_src"][k]]
+    valid = torch.zeros(R["Kp"], dtype=torch.bool)
+    valid[:32] = True
+    for f in range(R["n_freq"]):
+        for h in range(R["pe_chunks"]):
+            for e1 in range(16):
+                e = 16 * h + e1
+                k = 32 * (1 + f * R["pe_chunks"] + h) + 2 * e1
+                ang = base[:, R["pe_src"][e]] * float(1 << f)
+                internal[:, k], internal[:, k + 1] = torch.sin(ang), torch.cos(ang)
+                valid[k] = valid[k + 1] = f < R["pe_nf"][e]
+    ref_cols = [feat] + ([view] if mode != "MLP_Fea_noview" else [])
+    if mode in ("MLP_Fea_noview", "MLP_Fea") and fea_pe > 0:
+        ref_cols.append(orc.freq_encode(feat.double(), fea_pe))
+    if mode in ("MLP_Fea", "MLP") and view_pe > 0:
+        ref_cols.append(orc.freq_encode(view.double(), view_pe))
+    ref = torch.cat([c.double() for c in ref_cols], -1)
+    used = [p for p in R["perm"] if p >= 0]
+    assert sorted(used) == list(range(ref.shape[1])), "every reference column exactly once"
+    for k, src in enumerate(R["perm"]):
+        if src >= 0:
+            assert bool(valid[k]), (k, src)
+            assert torch.allclose(internal[:, k], ref[:, src], rtol=0, atol=1e-12), (k, src)
+
+
+def test_mma_recipe_rejects_heads_outside_the_envelope():
+    assert mma_recipe("MLP_Fea_noview", 30, 6, 0) is None        # app_dim > 29
+    assert mma_recipe("MLP_Fea", 27, 11, 0) is None              # more than 10 frequencies
+    assert nat.load().t2n_debug_mma_recipe(3, 27, 0, 0, (C.c_int * 1024)(), 1024) < 0      # SH head: no decoder

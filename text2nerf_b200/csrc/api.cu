@@ -364,6 +364,17 @@ int t2n_data_loss(const T2NOutputs* out, int R, int S, const float* rgb_gt, cons
     return rc;
 }
 
+int t2n_debug_mma_recipe(int shading, int app_dim, int fea_pe, int view_pe, int* out, int cap) {
+    MmaRecipe R;
+    if (!out || !build_mma_recipe(shading, app_dim, fea_pe, view_pe, R)) return T2N_E_BADARG;
+    const int need = 3 + 96 + R.Kp;
+    if (cap < need) return T2N_E_BADARG;
+    out[0] = R.n_freq; out[1] = R.pe_chunks; out[2] = R.Kp;
+    for (int i = 0; i < 32; ++i) { out[3 + i] = R.ident_src[i]; out[35 + i] = R.pe_src[i]; out[67 + i] = R.pe_nf[i]; }
+    for (int k = 0; k < R.Kp; ++k) out[99 + k] = R.perm[k];
+    return need;
+}
+
 int t2n_debug_chunk_program(int n_app_total, int Kp, unsigned char* out, int cap) {
     if (!out || n_app_total <= 0 || Kp < 32 || (Kp & 31) || cap < kMaxProg) return T2N_E_BADARG;
     const MmaPack P = mma_pack_layout(n_app_total, Kp);
