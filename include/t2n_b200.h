@@ -312,6 +312,9 @@ int t2n_debug_chunk_program(int n_app_total, int Kp, unsigned char* out, int cap
  * (perm[k] = column of the reference's mlp[0].weight that internal column k multiplies, -1 = zero weight).  Returns
  * the number of ints written, or a negative error code if the head is outside the tensor-core envelope. */
 int t2n_debug_mma_recipe(int shading, int app_dim, int fea_pe, int view_pe, int* out, int cap);
+/* Same for the column order of the tensor-core BACKWARD kernels (csrc/bwd_mma_defs.cuh build_mma_bwd_recipe):
+ * out = [own[32] (base-vector entry of identity slot s), perm[Kp]]. */
+int t2n_debug_mma_bwd_recipe(int shading, int app_dim, int fea_pe, int view_pe, int* out, int cap);
 /* Same, first n entries of the trace buffer (counters + the per-chunk timeline events of three iterations). */
 int t2n_debug_trace_read_n(long long* out, int n);
 int t2n_profile_read(int* ids, float* ms, int n);

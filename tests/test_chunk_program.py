@@ -179,3 +179,32 @@ def test_mma_recipe_rejects_heads_outside_the_envelope():
     assert mma_recipe("MLP_Fea_noview", 30, 6, 0) is None        # app_dim > 29
     assert mma_recipe("MLP_Fea", 27, 11, 0) is None              # more than 10 frequencies
     assert nat.load().t2n_debug_mma_recipe(3, 27, 0, 0, (C.c_int * 1024)(), 1024) < 0      # SH head: no decoder
+
+
+@pytest.mark.parametrize("mode,app_dim,fea_pe,view_pe", [
+    ("MLP_Fea_noview", 27, 6, 2), ("MLP_Fea_noview", 27, 0, 0), ("MLP_Fea_noview", 12, 3, 0), ("MLP_Fea", 27, 2, 2),
+    ("MLP_Fea", 27, 6, 4), ("MLP_Fea", 13, 5, 1), ("MLP_Fea", 27, 0, 3), ("MLP", 27, 6, 6), ("MLP", 27, 0, 0), ("MLP", 29, 0, 10)])
+def test_backward_recipe_is_a_reordering_of_the_forward_identity_chunk(mode, app_dim, fea_pe, view_pe):
+    """The backward kernels keep the forward's PE chunks and re-order the identity chunk so that the thread owning PE
+    entries {4ph.., 16+4ph..} also owns the identity columns of the same base entries (bwd_mma_defs.cuh): every reference
+    column must still be covered exactly once, identity slot s must point at the base entry of its PE entry, and no base
+    entry may appear in two slots."""
+    R = mma_recipe(mode, app_dim, fea_pe, view_pe)
+    buf = (C.c_int * 1024)()
+    n = nat.load().t2n_debug_mma_bwd_recipe(HEADS[mode], app_dim, fea_pe, view_pe, buf, 1024)
+    assert n == 32 + R["Kp"]
+    own, perm = list(buf[:32]), list(buf[32:n])
+    zero = app_dim + 6
+    assert perm[32:] == R["perm"][32:]                                  # PE chunks unchanged
+    assert sorted(p for p in perm if p >= 0) == sorted(p for p in R["perm"] if p >= 0)
+    for s in range(32):
+        ph, q = s >> 3, s & 7
+        e = 4 * ph + q if q < 4 else 16 + 4 * ph + (q - 4)
+        if R["pe_nf"][e] > 0:
+            assert own[s] == R["pe_src"][e], (s, e)
+    real = [b for b in own if b != zero]
+    assert len(real) == len(set(real)), "a base entry owned by two slots"
+    fwd_ident = {R["ident_src"][k]: R["perm"][k] for k in range(32) if R["perm"][k] >= 0}
+    for s in range(32):
+        assert perm[s] == fwd_ident.get(own[s], -1), s
+    assert set(fwd_ident) <= set(real)

@@ -128,6 +128,7 @@ SYMBOLS = {
     "t2n_debug_trace_read_n": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "t2n_debug_chunk_program": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int]),
     "t2n_debug_mma_recipe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "t2n_debug_mma_bwd_recipe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "t2n_profile_read": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
     "t2n_compute_alpha": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
                                     C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),

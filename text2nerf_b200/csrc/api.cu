@@ -375,6 +375,18 @@ int t2n_debug_mma_recipe(int shading, int app_dim, int fea_pe, int view_pe, int*
     return need;
 }
 
+int t2n_debug_mma_bwd_recipe(int shading, int app_dim, int fea_pe, int view_pe, int* out, int cap) {
+    MmaRecipe R;
+    MmaBwdRecipe B;
+    if (!out || !build_mma_recipe(shading, app_dim, fea_pe, view_pe, R) || !build_mma_bwd_recipe(R, app_dim, B))
+        return T2N_E_BADARG;
+    const int need = 32 + R.Kp;
+    if (cap < need) return T2N_E_BADARG;
+    for (int i = 0; i < 32; ++i) out[i] = B.own[i];
+    for (int k = 0; k < R.Kp; ++k) out[32 + k] = B.perm[k];
+    return need;
+}
+
 int t2n_debug_chunk_program(int n_app_total, int Kp, unsigned char* out, int cap) {
     if (!out || n_app_total <= 0 || Kp < 32 || (Kp & 31) || cap < kMaxProg) return T2N_E_BADARG;
     const MmaPack P = mma_pack_layout(n_app_total, Kp);
