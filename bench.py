@@ -191,7 +191,10 @@ class ClockSampler:
 
 
 def cpu_reference_leg(spec, params, rays_cpu, steps, warmup, what):
-    """Times the oracle on the host cores: bounded ray sample of the same workload."""
+    """Times the oracle on the host cores: bounded ray sample of the same workload.  Returns the sample size, the step
+    times and what the oracle computed on the sample (inputs + outputs), which the product arm compares its own result
+    for the SAME rays against (the `parity` block of the JSON line)."""
+    from oracle import ref_runner
     from oracle import t2n_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     S = orc.derive_step(spec)[1]
@@ -200,37 +203,116 @@ def cpu_reference_leg(spec, params, rays_cpu, steps, warmup, what):
     idx = torch.randperm(rays_cpu.shape[0], generator=g)[:n]
     rays = rays_cpu[idx].contiguous()
     times = []
+    # oracle/_ref (the unmodified reference modules, oracle/make_ref.py) when it travelled with the snapshot, else the port
+    ref_model = ref_runner.build(spec, params) if ref_runner.available() else None
+    kept = {"rays": rays, "S": S, "kind": "reference" if ref_model is not None else "port"}
     if what == "fwd":
         for i in range(warmup + steps):
             t0 = time.perf_counter()
             with torch.no_grad():
-                orc.render(spec, params, rays, S, False, True, None)
+                if ref_model is not None:
+                    out = ref_runner.render(ref_model, rays, S, False, True)
+                else:
+                    out = orc.render(spec, params, rays, S, False, True, None)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
+        kept.update(rgb_map=out[0], depth_map=out[1], z_vals=out[2], weight=out[3], weight_thres=spec.weight_thres)
     else:
-        p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-        jitter = torch.rand(n, 1, generator=g)
+        jitter_seed = 4321
+        torch.manual_seed(jitter_seed)
+        jitter = torch.rand(n, 1)                        # what tensorBase.py:316 draws after the same seed
         rgb_gt, depth_gt = torch.rand(n, 3, generator=g), 2 + 4 * torch.rand(n, generator=g)
+        if ref_model is not None:
+            p = dict(ref_model.named_parameters())
+        else:
+            p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
         for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            out = orc.render(spec, p, rays, S, True, True, jitter)
-            orc.training_loss(*out, rgb_gt, depth_gt).backward()
             for v in p.values():
                 v.grad = None
+            t0 = time.perf_counter()
+            if ref_model is not None:
+                out = ref_runner.render(ref_model, rays, S, True, True, jitter_seed=jitter_seed)
+            else:
+                out = orc.render(spec, p, rays, S, True, True, jitter)
+            loss = orc.training_loss(*out, rgb_gt, depth_gt)
+            loss.backward()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return n, times
+        kept.update(jitter=jitter, rgb_gt=rgb_gt, depth_gt=depth_gt, loss=float(loss),
+                    grads={k: v.grad for k, v in p.items()})
+    return n, times, kept
+
+
+def _psnr(a, b):
+    import math
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return 200.0 if mse == 0 else -10.0 * math.log10(mse)
+
+
+def parity_forward(model, dev, kept):
+    """The product arm's render of the oracle's ray sample of the timed view against what the oracle computed:
+    models/tensorBase.py:436-507 on identical rays and field.  Gates (BASELINE.json north_star): RGB 1e-4 relative,
+    PSNR within 0.05 dB; z_vals bit-exact."""
+    with torch.no_grad():
+        rgb, depth, z, w = [t.cpu() for t in model(kept["rays"].to(dev), is_train=False, white_bg=True, ndc_ray=0,
+                                                   N_samples=kept["S"])]
+    ref_rgb, ref_w = kept["rgb_map"], kept["weight"]
+    g = torch.Generator().manual_seed(5)
+    target = torch.rand(ref_rgb.shape, generator=g)          # any fixed image: PSNR(ours, t) against PSNR(reference, t)
+    out = {"sample": f"{ref_rgb.shape[0]} rays of the timed 800x800 view, S={kept['S']}, eval forward (the cpu_baseline sample)",
+           "rgb_max_rel": float(((rgb - ref_rgb).abs() / ref_rgb.abs().clamp_min(0.05)).max()),
+           "rgb_max_abs": float((rgb - ref_rgb).abs().max()),
+           "depth_max_rel": float(((depth - kept["depth_map"]).abs() / kept["depth_map"].abs().clamp_min(0.05)).max()),
+           "weight_max_abs": float((w - ref_w).abs().max()),
+           "z_bit_exact": bool(torch.equal(z, kept["z_vals"])),
+           "app_mask_flips": int(((w > kept["weight_thres"]) != (ref_w > kept["weight_thres"])).sum()),
+           "listed_samples": int((ref_w > kept["weight_thres"]).sum()),
+           "psnr_db": _psnr(rgb, ref_rgb),
+           "psnr_delta_db": abs(_psnr(rgb, target) - _psnr(ref_rgb, target))}
+    out["ok"] = bool(out["rgb_max_rel"] <= 1e-4 and out["z_bit_exact"] and out["psnr_delta_db"] <= 0.05
+                     and out["weight_max_abs"] <= 2e-6 and out["depth_max_rel"] <= 1e-4)
+    return out
+
+
+def parity_backward(model, dev, kept):
+    """Loss and all parameter gradients of the Text2NeRF data loss (text2nerf_main.py:563-575) on the oracle's training
+    sample, through the fused data_loss path with the oracle's jitter."""
+    from text2nerf_b200.tensorBase import _FusedLossFn
+    R, S = kept["rays"].shape[0], kept["S"]
+    model.zero_grad()
+    worst, worst_cos, per = 0.0, 1.0, {}
+    loss = None
+    for _ in range(2):      # the first pass sizes the tensor-core backward's capacity; the second is the one compared
+        model.zero_grad()
+        loss = _FusedLossFn.apply(model, kept["rays"].to(dev), kept["jitter"].reshape(-1).to(dev), S, True,
+                                  kept["rgb_gt"].to(dev), kept["depth_gt"].to(dev), 0.005, 1e3, 0.1, 1.0 / R,
+                                  True, *model._flat_params())[0]
+        loss.backward()
+        torch.cuda.synchronize()
+    for k, p in model.named_parameters():
+        a, b = p.grad.detach().double().cpu().flatten(), kept["grads"][k].double().flatten()
+        err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+        per[k] = [err, cos]
+        worst, worst_cos = max(worst, err), min(worst_cos, cos)
+    model.zero_grad()
+    out = {"sample": f"{R} rays, S={S}, fused data_loss + backward, {len(per)} parameter tensors",
+           "loss_rel": abs(float(loss) - kept["loss"]) / abs(kept["loss"]),
+           "grad_max_scaled_err": worst, "grad_min_cosine": worst_cos, "n_grads": len(per)}
+    out["ok"] = bool(out["loss_rel"] <= 2e-5 and worst <= 2e-4 and worst_cos > 1 - 1e-6)
+    return out
 
 
 def run_reference_arm(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path (the oracle port: same
-    ATen ops, tests pin it bit-exact to the unmodified reference) on the box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores: the unmodified
+    reference modules under oracle/_ref (oracle/make_ref.py; kind "reference"), else the oracle port (same ATen ops, tests
+    pin it bit-exact to the unmodified reference; kind "port")."""
     if rank != 0:
         return
     spec = oracle_spec()
     params = make_params()
     rays = host_rays(0)
-    n, times = cpu_reference_leg(spec, params, rays, args.steps, max(1, min(args.warmup, 1)), "fwd")
+    n, times, kept = cpu_reference_leg(spec, params, rays, args.steps, max(1, min(args.warmup, 1)), "fwd")
     total = sum(times)
     v = n * len(times) / total / 1e6
     cores = torch.get_num_threads()
@@ -238,7 +320,7 @@ def run_reference_arm(args, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "lego800: 300^3 VM field, 800x800 view, S=1036 (bounded CPU sample per step)"},
-            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kept["kind"],
                              "sample": f"{n} random rays of the 800x800 view per step, S=1036, eval forward"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -462,17 +544,21 @@ def main():
         launches_train = 16 * TRAIN_BATCHES_PER_STEP * args.steps    # march, pack, app, finalize, data_loss | pack_bwd, bwd-data, 4 wgrad, (pack_w1, ffma fallback, unpack: early exit), ray_backward
         model.enable_flat_grads(False)
 
-    # ---------------- CPU baseline (rank 0, N=1 only)
+    # ---------------- CPU baseline (rank 0, N=1 only) + parity of the product arm on the baseline's own ray samples
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         spec = oracle_spec()
-        n, times = cpu_reference_leg(spec, params, rays_pinned, 2, 1, "fwd")
-        cpu = {"value": n / min(times) / 1e6, "unit": "Mrays/s", "cores": torch.get_num_threads(), "kind": "port",
+        n, times, kept = cpu_reference_leg(spec, params, rays_pinned, 2, 1, "fwd")
+        cpu = {"value": n / min(times) / 1e6, "unit": "Mrays/s", "cores": torch.get_num_threads(), "kind": kept["kind"],
                "sample": f"{n} random rays of the same 800x800 view, S=1036, eval forward, best of 2 after 1 warm-up"}
+        parity = {"forward": parity_forward(model, dev, kept)}
         if not args.no_train:
-            nb, tb = cpu_reference_leg(spec, params, rays_pinned, 1, 1, "bwd")
+            nb, tb, kept_b = cpu_reference_leg(spec, params, rays_pinned, 1, 1, "bwd")
             cpu["fwd_bwd_value"] = nb / min(tb) / 1e6
             cpu["fwd_bwd_sample"] = f"{nb} rays, S=1036, loss of text2nerf_main.py:563-575 + backward"
+            parity["fwd_bwd"] = parity_backward(model, dev, kept_b)
+        parity["ok"] = all(v["ok"] for v in parity.values())
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -487,8 +573,11 @@ def main():
                         "d2h_bytes_per_step": n_rays * 16, "ms_per_step": ms_e2e / args.steps,
                         "api": "text2nerf_b200.OctreeRender_trilinear_fast(pinned host rays) + rgb/depth .cpu()"},
                 "gpu_launches": 4 * args.steps + launches_train,
-                "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "fwd_bwd": fwd_bwd}
+                "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "fwd_bwd": fwd_bwd}
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            print("bench.py: PARITY FAILED against the oracle on the timed workload: " + json.dumps(parity), file=sys.stderr)
+            sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 

@@ -262,3 +262,97 @@ def test_eval_render_is_independent_of_the_callers_chunk_size(cuda_device):
     assert merged[1] is None
     for got, ref in zip((merged[0], merged[2], merged[4], merged[3]), want):
         assert torch.equal(got, ref)
+
+
+# ---- the tensor-core kernels in steady state -----------------------------------------------------------------------
+# app_forward_mma_kernel / app_backward_mma_kernel stride 128-sample tiles over one persistent CTA per SM and pipeline
+# three consecutive tiles through 3-/4-deep rings.  A batch that lists >= 20 tiles per CTA exercises ring wrap, the
+# mbarrier phase parity after many chunks and the j-1 / j-2 overlap; the oracle checks every value that comes out.
+def _steady_state_case(seed=11):
+    spec, params, rays, jitter = _fog_case([64, 64, 64], [[-8, -8, -8], [8, 8, 8]], [0.5, 8.0], 1.0, 20480, seed,
+                                           [0.1, 0.0, -0.2], 0.5, gain=5.0)
+    return spec, params, rays, jitter, orc.derive_step(spec)[1] // 2
+
+
+def _require_tiles_per_cta(model, cuda_device, want=20):
+    listed = model.app_sample_count()[0]
+    sms = torch.cuda.get_device_properties(cuda_device).multi_processor_count
+    tiles_per_cta = listed / 128.0 / sms
+    assert tiles_per_cta >= want, f"only {tiles_per_cta:.1f} tiles per CTA ({listed} listed samples)"
+    return listed
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_forward_mma_steady_state_vs_oracle(train, cuda_device):
+    spec, params, rays, jitter, S = _steady_state_case()
+    ref = orc.render(spec, params, rays, S, train, True, jitter if train else None, None, keep=True)
+    model = build_model(spec, params, cuda_device)
+    assert model._mma_pack_buffer(cuda_device, model._native_field()) is not None, "case must be inside the tensor-core envelope"
+    with torch.no_grad():
+        out = render_with_jitter(model, rays.to(cuda_device), jitter if train else None, train, True, S)
+    _require_tiles_per_cta(model, cuda_device)
+    _check_forward(out, dict(rgb_map=ref[0], depth_map=ref[1], z_vals=ref[2], weight=ref[3]))
+    app = out[3].cpu() > spec.weight_thres
+    assert int((app != ref[4]["app_mask"]).sum()) <= 8          # isolated threshold flips out of ~400 k listed samples
+
+
+def test_backward_mma_steady_state_vs_oracle(cuda_device):
+    spec, params, rays, jitter, S = _steady_state_case(seed=12)
+    g = torch.Generator().manual_seed(78)
+    rgb_gt = torch.rand(rays.shape[0], 3, generator=g)
+    depth_gt = 0.5 + 7.5 * torch.rand(rays.shape[0], generator=g)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    loss_ref = orc.training_loss(*orc.render(spec, p_ref, rays, S, True, True, jitter), rgb_gt, depth_gt)
+    loss_ref.backward()
+    model = build_model(spec, params, cuda_device)
+    # two passes: the first one sizes the operand-image capacity from the listed-sample count, so that the second runs
+    # every tile through the tensor-core backward (none through the FFMA overflow path)
+    for _ in range(2):
+        model.zero_grad()
+        out = render_with_jitter(model, rays.to(cuda_device), jitter, True, True, S)
+        loss = orc.training_loss(*out, rgb_gt.to(cuda_device), depth_gt.to(cuda_device))
+        loss.backward()
+        torch.cuda.synchronize()
+    listed = _require_tiles_per_cta(model, cuda_device)
+    assert model._act_capacity(rays.shape[0], S) >= listed
+    assert abs(float(loss) - float(loss_ref)) <= 2e-5 * abs(float(loss_ref))
+    for k, p in model.named_parameters():
+        gr = p_ref[k].grad
+        assert scaled_err(p.grad, gr) <= 2e-4, (k, scaled_err(p.grad, gr))
+        assert cosine(p.grad, gr) > 1 - 1e-6, k
+
+
+def test_forward_backward_vs_oracle_at_bench_shape(cuda_device):
+    """BASELINE configs 2-5's real shape -- 300^3 field, box +-1.5 at z 2.5..5.5, S=1036 -- on 512 random rays of the
+    800x800 view: forward (eval and train) and all 19 gradients against the oracle."""
+    spec = orc.FieldSpec(aabb=[[-1.5, -1.5, 2.5], [1.5, 1.5, 5.5]], grid=[300, 300, 300], near_far=[2.0, 6.0],
+                         step_ratio=0.5)
+    params = orc.init_params(spec, seed=0, density_gain=10.8, app_gain=1.0)
+    S = orc.derive_step(spec)[1]
+    assert S == 1036
+    g = torch.Generator().manual_seed(9)
+    R = 512
+    px = torch.rand(R, 2, generator=g) * 800.0
+    d = torch.cat([(px - 400.0) / 1111.1, torch.ones(R, 1)], -1)
+    rays = torch.cat([torch.zeros(R, 3), d / d.norm(dim=-1, keepdim=True)], -1).contiguous()
+    jitter = torch.rand(R, 1, generator=g)
+    model = build_model(spec, params, cuda_device)
+    ref = orc.render(spec, params, rays, S, False, True, None)
+    with torch.no_grad():
+        out = render_with_jitter(model, rays.to(cuda_device), None, False, True, S)
+    _check_forward(out, dict(rgb_map=ref[0], depth_map=ref[1], z_vals=ref[2], weight=ref[3]))
+    rgb_gt = torch.rand(R, 3, generator=g)
+    depth_gt = 2.0 + 4.0 * torch.rand(R, generator=g)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref_t = orc.render(spec, p_ref, rays, S, True, True, jitter)
+    loss_ref = orc.training_loss(*ref_t, rgb_gt, depth_gt)
+    loss_ref.backward()
+    out = render_with_jitter(model, rays.to(cuda_device), jitter, True, True, S)
+    _check_forward(out, dict(rgb_map=ref_t[0].detach(), depth_map=ref_t[1].detach(), z_vals=ref_t[2], weight=ref_t[3].detach()))
+    loss = orc.training_loss(*out, rgb_gt.to(cuda_device), depth_gt.to(cuda_device))
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 2e-5 * abs(float(loss_ref))
+    for k, p in model.named_parameters():
+        gr = p_ref[k].grad
+        assert scaled_err(p.grad, gr) <= 2e-4, (k, scaled_err(p.grad, gr))
+        assert cosine(p.grad, gr) > 1 - 1e-6, k

@@ -71,9 +71,12 @@ def sharded_train_step(model, optimizer, rays, targets_fn, n_samples, rank: int,
     if seed is not None:
         torch.manual_seed(seed)
     jitter_full = torch.rand(R, 1)                      # same CPU draw on every rank (tensorBase.py:316)
+    # tensorBase.py:497: training composites a white background at random when white_bg is False; the draw follows the
+    # jitter draw like in TensorBase.forward and is identical on every rank (same seed)
+    white = bool(white_bg) or bool(torch.rand((1,)) < 0.5)
     from .tensorBase import _RenderFn
     out = _RenderFn.apply(model, rays[lo:hi].contiguous(), jitter_full[lo:hi].to(rays.device).view(-1).contiguous(),
-                          n_samples, True, bool(white_bg), True, *model._flat_params())
+                          n_samples, True, white, True, *model._flat_params())
     loss = targets_fn(lo, hi, out) * world               # undo the 1/world of the all-reduce average
     loss.backward()
     allreduce_flat_grads(model, world)

@@ -211,6 +211,7 @@ class TensorVMSplit(TensorBase):
         self.app_plane, self.app_line = self.up_sampling_VM(self.app_plane, self.app_line, res_target)
         self.density_plane, self.density_line = self.up_sampling_VM(self.density_plane, self.density_line, res_target)
         self.update_stepSize(res_target)
+        self._refresh_flat_grads()
         print(f'upsamping to {res_target}')
 
     @torch.no_grad()
@@ -239,6 +240,7 @@ class TensorVMSplit(TensorBase):
         new_size = hi - lo
         self.aabb = new_aabb
         self.update_stepSize((int(new_size[0]), int(new_size[1]), int(new_size[2])))
+        self._refresh_flat_grads()
 
     # ---- native glue -------------------------------------------------------------------------------
     def _flat_params(self) -> List[torch.Tensor]:
@@ -278,6 +280,13 @@ class TensorVMSplit(TensorBase):
         enable_flat_grads() they are views into one flat fp32 buffer (the NCCL all-reduce buffer)."""
         flat = getattr(self, "_flat_grad", None)
         if flat is not None:
+            # the kernels scatter with the field's CURRENT grid sizes into raw pointers: a view that no longer matches
+            # its parameter (factors replaced by upsample / shrink / load without re-enabling) would be written out of
+            # bounds, so refuse it here
+            for v, t in zip(flat["views"], p_cl):
+                if v.shape != t.shape or v.stride() != t.stride():
+                    raise RuntimeError("flat gradient buffer is stale: a parameter changed shape/layout "
+                                       f"({tuple(v.shape)} vs {tuple(t.shape)}); call enable_flat_grads() again")
             return flat["views"]            # the trainer zeroes the flat buffer once per step
         return [torch.zeros_like(t) for t in p_cl]
 
@@ -322,6 +331,15 @@ class TensorVMSplit(TensorBase):
             views.append(torch.as_strided(buf, t.shape, t.stride(), off))
         self._flat_grad = {"buffer": buf, "views": views}
         return buf
+
+    def _refresh_flat_grads(self):
+        """The factor Parameters were replaced (upsample_volume_grid / shrink): rebuild the flat gradient buffer and its
+        views for the new sizes.  Holders of the old buffer must fetch the new one (enable_flat_grads returns it, and
+        model._flat_grad["buffer"] is what dist.allreduce_flat_grads reads)."""
+        if getattr(self, "_flat_grad", None) is not None:
+            for p in self._flat_params():
+                p.grad = None
+            self.enable_flat_grads(True)
 
     def app_sample_count(self) -> int:
         """Samples that passed the weight threshold / the validity test in the last forward

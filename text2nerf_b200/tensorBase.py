@@ -81,15 +81,22 @@ class AlphaGridMask(torch.nn.Module):
         return F.grid_sample(self.alpha_volume, grid, align_corners=True).view(-1)
 
     def native(self) -> nat.T2NAlphaMask:
+        """The C-ABI view of the mask.  Built once per (volume, box) pair: reading `aabb` / `invgridSize` back to the
+        host costs device syncs, which the render path must not pay on every call."""
         vol = self.alpha_volume
         if vol.dtype != torch.float32 or not vol.is_contiguous():
             vol = vol.float().contiguous()
             self.alpha_volume = vol
+        key = (vol.data_ptr(), tuple(vol.shape), self.aabb.data_ptr(), self.aabb._version, vol.device)
+        cached = self.__dict__.get("_native_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
         m = nat.T2NAlphaMask()
         m.volume = vol.data_ptr()
         m.dims = nat.I3(vol.shape[-1], vol.shape[-2], vol.shape[-3])
         m.aabb_lo = nat.F3(*self.aabb[0].tolist())
         m.inv_size = nat.F3(*self.invgridSize.tolist())
+        self.__dict__["_native_cache"] = (key, m)
         return m
 
 
@@ -395,6 +402,40 @@ class _FusedLossFn(torch.autograd.Function):
         return (None,) * 12 + tuple(model._grads_for_autograd(grads))
 
 
+class _ListedCountPoll:
+    """Asynchronous device->host reads of the listed-sample counter: pinned buffers + events, kept OUTSIDE the module's
+    tensors/state so that copy.deepcopy / pickling / torch.save of the module see a fresh, empty poller."""
+
+    def __init__(self):
+        self.pool, self.pending = None, []
+
+    def post(self, counters, n_rays):
+        if len(self.pending) >= 4:
+            return
+        dev = counters.device
+        with torch.cuda.device(dev):
+            if self.pool is None:
+                self.pool = [(torch.empty((8,), dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            host, ev = self.pool.pop(0)
+            host.copy_(counters, non_blocking=True)
+            ev.record(torch.cuda.current_stream(dev))
+        self.pending.append((host, ev, max(1, int(n_rays))))
+
+    def poll(self):
+        done = []
+        while self.pending and self.pending[0][1].query():
+            host, ev, n_rays = self.pending.pop(0)
+            done.append((float(host[0]), n_rays))
+            self.pool.append((host, ev))
+        return done
+
+    def __deepcopy__(self, memo):
+        return _ListedCountPoll()
+
+    def __reduce__(self):
+        return (_ListedCountPoll, ())
+
+
 # ------------------------------------------------------------------------------------------------
 # TensorBase
 # ------------------------------------------------------------------------------------------------
@@ -645,11 +686,7 @@ class TensorBase(torch.nn.Module):
                                "MLP_PE is not runnable in the reference either (tensorBase.py:115 vs :124-130)")
         if not rays_chunk.is_cuda:
             raise nat.NativeLibraryError("text2nerf_b200 renders on a CUDA device only; rays are on " + str(rays_chunk.device))
-        rays = rays_chunk.detach()
-        if rays.dtype != torch.float32 or not rays.is_contiguous() or rays.shape[-1] != 6:
-            rays = rays[..., :6].float().contiguous() if rays.shape[-1] >= 6 else rays
-        if rays.dim() != 2 or rays.shape[-1] != 6:
-            raise ValueError("rays_chunk must be [R,6+] (origin, direction)")
+        rays = self._check_rays(rays_chunk)
         R = rays.shape[0]
         S = int(N_samples) if N_samples > 0 else self.nSamples
         jitter = None
@@ -671,6 +708,19 @@ class TensorBase(torch.nn.Module):
                 lst.append(t)
         return tuple(torch.cat(x) for x in outs)
 
+    @staticmethod
+    def _check_rays(rays_chunk):
+        """[R,6] float32 contiguous rays.  The reference's depth term reads the LAST ray column (tensorBase.py:505),
+        which is d_z for the 6-column rays of the Text2NeRF flow and what the kernels use; wider rays (the 8-column
+        nsvf / tankstemple loaders, outside this flow) would silently change depth_map, so they are refused."""
+        rays = rays_chunk.detach()
+        if rays.dim() != 2 or rays.shape[-1] != 6:
+            raise ValueError(f"rays_chunk must be [R,6] (origin, direction); got {tuple(rays.shape)}: the depth "
+                             "background term uses the last column (tensorBase.py:505), only 6-column rays are built")
+        if rays.dtype != torch.float32 or not rays.is_contiguous():
+            rays = rays.float().contiguous()
+        return rays
+
     def data_loss(self, rays_chunk, rgb_gt, depth_gt, white_bg=True, N_samples=-1, w_depth=0.005, w_trans=1e3,
                   delta=0.1, n_rays_total=None, return_terms=False):
         """Fused fast path of one training step's data terms (text2nerf_main.py:556-575):
@@ -689,9 +739,7 @@ class TensorBase(torch.nn.Module):
             raise RuntimeError("MLP_PE is not runnable in the reference either (tensorBase.py:115 vs :124-130)")
         if not rays_chunk.is_cuda:
             raise nat.NativeLibraryError("text2nerf_b200 renders on a CUDA device only; rays are on " + str(rays_chunk.device))
-        rays = rays_chunk.detach()[..., :6].float().contiguous()
-        if rays.dim() != 2 or rays.shape[-1] != 6:
-            raise ValueError("rays_chunk must be [R,6+] (origin, direction)")
+        rays = self._check_rays(rays_chunk)
         R = rays.shape[0]
         S = int(N_samples) if N_samples > 0 else self.nSamples
         if R > ((1 << 31) - 1) // S:
@@ -784,26 +832,16 @@ class TensorBase(torch.nn.Module):
         return max(128, (rows + 127) // 128 * 128)
 
     def _post_listed_count(self, counters, R):
-        pend = getattr(self, "_listed_pending", None)
-        if pend is None:
-            pend = self._listed_pending = []
-        if len(pend) >= 4:
-            return
-        pool = getattr(self, "_listed_pool", None)
-        if pool is None:
-            pool = self._listed_pool = [(torch.empty((8,), dtype=torch.int32).pin_memory(), torch.cuda.Event())
-                                        for _ in range(4)]
-        host, ev = pool.pop(0)
-        host.copy_(counters, non_blocking=True)
-        ev.record()
-        pend.append((host, ev, max(1, int(R))))
+        side = self.__dict__.get("_listed_side")
+        if side is None:
+            side = self.__dict__["_listed_side"] = _ListedCountPoll()
+        side.post(counters, R)
 
     def _poll_listed_count(self):
-        pend = getattr(self, "_listed_pending", None)
-        while pend and pend[0][1].query():
-            host, ev, n_rays = pend.pop(0)
-            self._listed_per_ray = max(0.98 * getattr(self, "_listed_per_ray", 0.0), float(host[0]) / n_rays)
-            self._listed_pool.append((host, ev))
+        side = self.__dict__.get("_listed_side")
+        if side is not None:
+            for listed, n_rays in side.poll():
+                self._listed_per_ray = max(0.98 * getattr(self, "_listed_per_ray", 0.0), listed / n_rays)
 
     def _w1_packed_buffer(self, device):
         if not self._is_mlp:
