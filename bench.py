@@ -238,9 +238,20 @@ def cpu_reference_leg(spec, params, rays_cpu, steps, warmup, what):
             loss.backward()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-        kept.update(jitter=jitter, rgb_gt=rgb_gt, depth_gt=depth_gt, loss=float(loss),
-                    grads={k: v.grad for k, v in p.items()})
+        kept.update(jitter=jitter, rgb_gt=rgb_gt, depth_gt=depth_gt, loss=float(loss.detach()),
+                    grads={k: v.grad for k, v in p.items()}, weight=out[3].detach(), weight_thres=spec.weight_thres)
     return n, times, kept
+
+
+def cpu_reference_regrad(spec, params, kept, selection):
+    """Part of the CPU leg (checker role): loss and gradients of the reference's function on a given app-sample
+    selection (oracle port, render(app_mask_override=...))."""
+    from oracle import t2n_oracle as orc
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    out = orc.render(spec, p, kept["rays"], kept["S"], True, True, kept["jitter"], None, app_mask_override=selection)
+    loss = orc.training_loss(*out, kept["rgb_gt"], kept["depth_gt"])
+    loss.backward()
+    return dict(kept, loss=float(loss.detach()), grads={k: v.grad for k, v in p.items()})
 
 
 def _psnr(a, b):
@@ -274,11 +285,21 @@ def parity_forward(model, dev, kept):
     return out
 
 
-def parity_backward(model, dev, kept):
+def parity_backward(model, dev, kept, spec, params):
     """Loss and all parameter gradients of the Text2NeRF data loss (text2nerf_main.py:563-575) on the oracle's training
-    sample, through the fused data_loss path with the oracle's jitter."""
-    from text2nerf_b200.tensorBase import _FusedLossFn
+    sample, through the fused data_loss path with the oracle's jitter.  The selection weight > rayMarch_weight_thres
+    (tensorBase.py:477) is a discontinuity of the reference's function: when isolated samples within fp32 noise of the
+    threshold are selected differently, the reference gradients are re-evaluated (oracle port) on the product arm's
+    selection, and the number of such samples is reported."""
+    from text2nerf_b200.tensorBase import _FusedLossFn, _RenderFn
     R, S = kept["rays"].shape[0], kept["S"]
+    with torch.no_grad():
+        w = _RenderFn.apply(model, kept["rays"].to(dev), kept["jitter"].reshape(-1).to(dev), S, True, True, False,
+                            *model._flat_params())[3].cpu()
+    sel = w > kept["weight_thres"]
+    flips = int((sel != (kept["weight"] > kept["weight_thres"])).sum())
+    if 0 < flips <= 8:
+        kept = cpu_reference_regrad(spec, params, kept, sel)
     model.zero_grad()
     worst, worst_cos, per = 0.0, 1.0, {}
     loss = None
@@ -298,7 +319,7 @@ def parity_backward(model, dev, kept):
     model.zero_grad()
     out = {"sample": f"{R} rays, S={S}, fused data_loss + backward, {len(per)} parameter tensors",
            "loss_rel": abs(float(loss) - kept["loss"]) / abs(kept["loss"]),
-           "grad_max_scaled_err": worst, "grad_min_cosine": worst_cos, "n_grads": len(per)}
+           "grad_max_scaled_err": worst, "grad_min_cosine": worst_cos, "n_grads": len(per), "app_mask_flips": flips}
     out["ok"] = bool(out["loss_rel"] <= 2e-5 and worst <= 2e-4 and worst_cos > 1 - 1e-6)
     return out
 
@@ -557,7 +578,7 @@ def main():
             nb, tb, kept_b = cpu_reference_leg(spec, params, rays_pinned, 1, 1, "bwd")
             cpu["fwd_bwd_value"] = nb / min(tb) / 1e6
             cpu["fwd_bwd_sample"] = f"{nb} rays, S=1036, loss of text2nerf_main.py:563-575 + backward"
-            parity["fwd_bwd"] = parity_backward(model, dev, kept_b)
+            parity["fwd_bwd"] = parity_backward(model, dev, kept_b, spec, params)
         parity["ok"] = all(v["ok"] for v in parity.values())
 
     if rank == 0:

@@ -313,11 +313,15 @@ def alpha_mask_lookup(mask_volume, mask_aabb, pts):
 
 def render(spec: FieldSpec, params: Dict[str, torch.Tensor], rays, n_samples: int = -1,
            is_train: bool = False, white_bg: bool = True, jitter: Optional[torch.Tensor] = None,
-           alpha_mask=None, keep: bool = False):
+           alpha_mask=None, keep: bool = False, app_mask_override: Optional[torch.Tensor] = None):
     """TensorBase.forward for ndc_ray=False (models/tensorBase.py:436-507).
 
     ``rays`` [R,6] = origin, direction.  ``jitter`` must be given iff is_train.
     ``alpha_mask`` = (volume[1,1,Z,Y,X], aabb[2,3]) or None.
+    ``app_mask_override`` [R,S] bool replaces the selection ``weight > rayMarch_weight_thres`` of tensorBase.py:477: the
+    selection is a discontinuity of the reference's function (a weight within fp32 noise of the threshold flips it even
+    between the reference in fp32 and in fp64), so gradient comparisons evaluate the reference's function
+    on the selection the implementation under test made whenever the two selections differ in isolated samples.
     Returns (rgb_map[R,3], depth_map[R], z_vals[R,S], weight[R,S]) and, with
     keep=True, a dict of intermediates as a fifth element."""
     if is_train and jitter is None:
@@ -351,6 +355,8 @@ def render(spec: FieldSpec, params: Dict[str, torch.Tensor], rays, n_samples: in
 
     alpha, weight, bg = alpha_composite(sigma, dists * spec.distance_scale)
     app_mask = weight > spec.weight_thres
+    if app_mask_override is not None:
+        app_mask = app_mask_override
     if app_mask.any():                                           # tensorBase.py:489-492
         feat = app_feature(params, xn[app_mask])
         rgb[app_mask] = decode_rgb(spec, params, xn[app_mask], viewdirs[app_mask], feat)
