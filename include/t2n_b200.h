@@ -32,7 +32,7 @@ extern "C" {
 
 typedef struct CUstream_st* t2n_stream_t;   /* == cudaStream_t */
 
-#define T2N_ABI_VERSION 8
+#define T2N_ABI_VERSION 9
 
 enum {
     T2N_E_BADARG   = -1,   /* null pointer / non-positive size */
@@ -291,6 +291,37 @@ int t2n_rotate_rays(const float* c2w_host, const float* directions, int n, float
  * (models/tensorBase.py:413-433) used by getDenseAlpha/updateAlphaMask.  alpha [n]. */
 int t2n_compute_alpha(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
                       const float* xyz, int n, float length, float* alpha, t2n_stream_t stream);
+
+/* ---- grid maintenance of a TensoRF-style coarse-to-fine run ----------------------------- */
+
+/* TensorBase.getDenseAlpha (models/tensorBase.py:328-344): alpha = 1 - exp(-sigma * length) of every voxel of a
+ * (gx, gy, gz) occupancy grid spanning the field's box, through the current alpha mask if there is one.  sx/sy/sz are
+ * the three linspace(0, 1, g) vectors (device, made by the caller like the reference makes them); voxel (i,j,k) sits at
+ * aabb_lo * (1 - s) + aabb_hi * s.  Outputs (each may be NULL): alpha_xyz [gx][gy][gz] (getDenseAlpha's return),
+ * alpha_zyx [gz][gy][gx] clamped to [0,1] (the layout updateAlphaMask pools), xyz [gx][gy][gz][3]. */
+int t2n_dense_alpha(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                    const float* sx, const float* sy, const float* sz, int gx, int gy, int gz, float length,
+                    float* alpha_xyz, float* alpha_zyx, float* xyz, t2n_stream_t stream);
+
+/* The rest of TensorBase.updateAlphaMask (models/tensorBase.py:352-366): F.max_pool3d(kernel 3, stride 1, padding 1)
+ * of alpha_zyx, threshold (>= thres -> 1, else 0) into mask [gz][gy][gx], and the index bounding box of the occupied
+ * voxels: bbox8 (device, 8 ints) = min ix, iy, iz, max ix, iy, iz, occupied count, 0. */
+int t2n_alpha_pool_mask(const float* alpha_zyx, int gx, int gy, int gz, float thres, float* mask, int32_t* bbox8,
+                        t2n_stream_t stream);
+
+/* TensorBase.filtering_rays (models/tensorBase.py:372-404) on n rays [n][6]: keep[r] = 1 if the ray passes.
+ * bbox_only != 0: slab test against the field's box; else: any of the ray's n_samples evaluation samples
+ * (sample_ray, is_train=False) sees alpha > 0 in the mask (mask must be given). */
+int t2n_filter_rays(const T2NField* field, const T2NAlphaMask* mask, const float* rays, long long n, int n_samples,
+                    int bbox_only, unsigned char* keep, t2n_stream_t stream);
+
+/* TensorVMSplit.up_sampling_VM (models/tensoRF.py:243-256): F.interpolate(bilinear, align_corners=True) of one
+ * texel-major factor [H][W][C] -> [H2][W2][C] (lines: W = W2 = 1).  C % 4 == 0. */
+int t2n_resample_plane(const float* src, int H, int W, int C, float* dst, int H2, int W2, t2n_stream_t stream);
+
+/* TensorVMSplit.shrink (models/tensoRF.py:266-290): dst[y][x][:] = src[y0 + y][x0 + x][:], texel-major. */
+int t2n_crop_plane(const float* src, int H, int W, int C, int y0, int x0, float* dst, int H2, int W2,
+                   t2n_stream_t stream);
 
 /* Measurement aid (bench.py roofline leg; not part of the reference surface).  While enabled,
  * every forward/backward call records CUDA events on its stream around each kernel it launches.

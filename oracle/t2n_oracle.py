@@ -290,6 +290,40 @@ def decode_rgb(spec: FieldSpec, params, xn, viewdirs, feat):
     return torch.sigmoid(h)
 
 
+def decoder_preactivations(spec: FieldSpec, params, xn, viewdirs, feat):
+    """(h1, h2): the two hidden pre-activations of the MLP heads (models/tensorBase.py:94-96) for given samples.
+    Used by gradient-parity checks to find samples that sit on a ReLU kink: d relu / dh flips when an implementation's
+    h differs from the reference's by more than |h| (fp32 summation order moves h by up to ~2e-6 here), and the
+    gradient of such a sample changes by a finite amount -- in the reference as much as in any re-implementation."""
+    mode = spec.shading
+    cols = [feat] if mode == "MLP_Fea_noview" else [feat, viewdirs]
+    if mode in ("MLP_Fea_noview", "MLP_Fea") and spec.fea_pe > 0:
+        cols.append(freq_encode(feat, spec.fea_pe))
+    if mode in ("MLP_Fea", "MLP") and spec.view_pe > 0:
+        cols.append(freq_encode(viewdirs, spec.view_pe))
+    h1 = F.linear(torch.cat(cols, dim=-1), params["renderModule.mlp.0.weight"], params["renderModule.mlp.0.bias"])
+    h2 = F.linear(torch.relu(h1), params["renderModule.mlp.2.weight"], params["renderModule.mlp.2.bias"])
+    return h1, h2
+
+
+def relu_kink_samples(spec: FieldSpec, params, rays, aux, eps: float = 4e-6):
+    """Number of listed samples (aux = render(..., keep=True)[4]) with a hidden unit within eps of a ReLU kink, and
+    the largest compositing weight among them."""
+    m = aux["app_mask"]
+    if spec.shading not in ("MLP_Fea_noview", "MLP_Fea", "MLP") or not bool(m.any()):
+        return 0, 0.0
+    xn = aux["xn"][m]
+    viewdirs = rays[:, 3:6].view(-1, 1, 3).expand(aux["xn"].shape)[m]
+    with torch.no_grad():
+        p = {k: v.detach() for k, v in params.items()}
+        h1, h2 = decoder_preactivations(spec, p, xn, viewdirs, app_feature(p, xn))
+        near = (h1.abs().min(dim=1).values < eps) | (h2.abs().min(dim=1).values < eps)
+    if not bool(near.any()):
+        return 0, 0.0
+    w = aux.get("weight_listed")
+    return int(near.sum()), float(w[near].max()) if w is not None else float("nan")
+
+
 # ----------------------------------------------------------------------------------------------
 # compositing
 # ----------------------------------------------------------------------------------------------
@@ -370,7 +404,7 @@ def render(spec: FieldSpec, params: Dict[str, torch.Tensor], rays, n_samples: in
     depth_map = depth_map + (1. - acc) * rays[..., -1]           # last ray column = d_z (tensorBase.py:505)
     if keep:
         aux = dict(sigma=sigma, alpha=alpha, valid=valid, app_mask=app_mask, rgb=rgb, acc=acc,
-                   bg=bg, xn=xn, sigma_feat=sigma_feat)
+                   bg=bg, xn=xn, sigma_feat=sigma_feat, weight_listed=weight.detach()[app_mask])
         return rgb_map, depth_map, z, weight, aux
     return rgb_map, depth_map, z, weight
 

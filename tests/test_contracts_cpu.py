@@ -36,7 +36,7 @@ def test_product_package_never_imports_the_oracle():
 def test_bench_touches_the_oracle_only_in_its_cpu_legs():
     hits = _oracle_imports(os.path.join(ROOT, "bench.py"))
     assert hits, "the cpu_baseline / --impl reference legs run the oracle"
-    assert {fn for fn, _ in hits} <= {"oracle_spec", "cpu_reference_leg", "cpu_reference_regrad"}, hits
+    assert {fn for fn, _ in hits} <= {"oracle_spec", "cpu_reference_leg", "cpu_reference_regrad", "cpu_reference_kinks"}, hits
 
 
 def test_reference_arm_prints_the_contract_line():

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import Case, build_model, cosine, golden_names, rel_err, render_with_jitter, scaled_err
+from helpers import Case, build_model, check_grads, cosine, golden_names, rel_err, render_with_jitter, scaled_err
 from oracle import t2n_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -306,8 +306,10 @@ def test_backward_mma_steady_state_vs_oracle(cuda_device):
     rgb_gt = torch.rand(rays.shape[0], 3, generator=g)
     depth_gt = 0.5 + 7.5 * torch.rand(rays.shape[0], generator=g)
     p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    loss_ref = orc.training_loss(*orc.render(spec, p_ref, rays, S, True, True, jitter), rgb_gt, depth_gt)
+    ref = orc.render(spec, p_ref, rays, S, True, True, jitter, None, keep=True)
+    loss_ref = orc.training_loss(*ref[:4], rgb_gt, depth_gt)
     loss_ref.backward()
+    kinks, _ = orc.relu_kink_samples(spec, params, rays, ref[4])
     model = build_model(spec, params, cuda_device)
     # two passes: the first one sizes the operand-image capacity from the listed-sample count, so that the second runs
     # every tile through the tensor-core backward (none through the FFMA overflow path)
@@ -320,10 +322,7 @@ def test_backward_mma_steady_state_vs_oracle(cuda_device):
     listed = _require_tiles_per_cta(model, cuda_device)
     assert model._act_capacity(rays.shape[0], S) >= listed
     assert abs(float(loss) - float(loss_ref)) <= 2e-5 * abs(float(loss_ref))
-    for k, p in model.named_parameters():
-        gr = p_ref[k].grad
-        assert scaled_err(p.grad, gr) <= 2e-4, (k, scaled_err(p.grad, gr))
-        assert cosine(p.grad, gr) > 1 - 1e-6, k
+    check_grads(model, {k: v.grad for k, v in p_ref.items()}, kink_samples=kinks)
 
 
 def test_forward_backward_vs_oracle_at_bench_shape(cuda_device):
@@ -369,7 +368,18 @@ def test_forward_backward_vs_oracle_at_bench_shape(cuda_device):
     loss_ref = orc.training_loss(*ref_t[:4], rgb_gt, depth_gt)
     loss_ref.backward()
     assert abs(float(loss) - float(loss_ref)) <= 2e-5 * abs(float(loss_ref))
-    for k, p in model.named_parameters():
-        gr = p_ref[k].grad
-        assert scaled_err(p.grad, gr) <= 2e-4, (k, scaled_err(p.grad, gr))
-        assert cosine(p.grad, gr) > 1 - 1e-6, k
+    # this seed has one listed sample (ray 229, k = 62, weight 0.068) whose hidden unit 40 of layer 1 sits at
+    # h1 = -1.6e-6: the tensor-core decoder lands on the other side of the kink (tools/diag_bisect.py)
+    kinks, w_max = orc.relu_kink_samples(spec, params, rays, ref_t[4])
+    assert kinks >= 1
+    check_grads(model, {k: v.grad for k, v in p_ref.items()}, kink_samples=kinks)
+    # the exact FFMA decoder (T2N_DECODER=ffma: fp32 FFMA h, no tensor cores) stays on the reference's side of that kink
+    import os
+    os.environ["T2N_DECODER"] = "ffma"
+    try:
+        model.zero_grad()
+        out = render_with_jitter(model, rays.to(cuda_device), jitter, True, True, S)
+        orc.training_loss(*out, rgb_gt.to(cuda_device), depth_gt.to(cuda_device)).backward()
+        check_grads(model, {k: v.grad for k, v in p_ref.items()}, kink_samples=0)
+    finally:
+        del os.environ["T2N_DECODER"]

@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libt2n_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class NativeLibraryError(RuntimeError):
@@ -130,6 +130,15 @@ SYMBOLS = {
     "t2n_debug_mma_recipe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "t2n_debug_mma_bwd_recipe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "t2n_profile_read": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
+    "t2n_dense_alpha": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "t2n_alpha_pool_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "t2n_filter_rays": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NAlphaMask), C.c_void_p, C.c_longlong, C.c_int,
+                                  C.c_int, C.c_void_p, C.c_void_p]),
+    "t2n_resample_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "t2n_crop_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p]),
     "t2n_compute_alpha": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
                                     C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
 }

@@ -6,6 +6,7 @@
 #include <cmath>
 #include "launch.h"
 #include "rays.cuh"
+#include "maintenance.cuh"
 
 using namespace t2n;
 
@@ -300,7 +301,7 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
             const int smem_bytes = mma_smem_layout().total;
             if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
             g_prof.start(2, st);
-            rc = launch_app_forward_mma(ma2, smem_bytes, dev.sm_count, st);
+            rc = launch_app_forward_mma(ma2, smem_bytes, getenv("T2N_FWD_GRID") ? atoi(getenv("T2N_FWD_GRID")) : dev.sm_count, st);
             g_prof.stop(st);
             if (rc) return rc;
         } else {
@@ -550,7 +551,7 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
             const int smem_bd = bwd_smem_layout().total;
             if (smem_bd > dev.max_smem_optin) return T2N_E_SHADING;
             g_prof.start(8, st);
-            rc = launch_app_backward_mma(d, smem_bd, dev.sm_count, st);
+            rc = launch_app_backward_mma(d, smem_bd, getenv("T2N_BWD_GRID") ? atoi(getenv("T2N_BWD_GRID")) : dev.sm_count, st);
             g_prof.stop(st);
             if (rc) return rc;
 
@@ -695,6 +696,69 @@ int t2n_compute_alpha(const T2NField* field, const T2NParams* params, const T2NA
     a.xyz = xyz; a.n = n; a.length = length; a.alpha = alpha;
     alpha_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
+}
+
+int t2n_dense_alpha(const T2NField* field, const T2NParams* params, const T2NAlphaMask* mask,
+                    const float* sx, const float* sy, const float* sz, int gx, int gy, int gz, float length,
+                    float* alpha_xyz, float* alpha_zyx, float* xyz, t2n_stream_t stream) {
+    if (!field || !params || !sx || !sy || !sz || gx <= 0 || gy <= 0 || gz <= 0) return T2N_E_BADARG;
+    if (!alpha_xyz && !alpha_zyx && !xyz) return T2N_E_BADARG;
+    for (int i = 0; i < 3; ++i) {
+        if (field->n_sigma[i] <= 0 || field->n_sigma[i] % 4) return T2N_E_LAYOUT;
+        if (!params->sigma_plane[i] || !params->sigma_line[i]) return T2N_E_BADARG;
+    }
+    DenseAlphaArgs a;
+    memset(&a, 0, sizeof(a));
+    a.f = make_field_dev(field, mask);
+    for (int i = 0; i < 3; ++i) { a.sp[i] = params->sigma_plane[i]; a.sl[i] = params->sigma_line[i]; a.sc[i] = field->n_sigma[i]; }
+    a.sx = sx; a.sy = sy; a.sz = sz; a.gx = gx; a.gy = gy; a.gz = gz; a.length = length;
+    a.alpha_xyz = alpha_xyz; a.alpha_zyx = alpha_zyx; a.xyz = xyz;
+    return launch_dense_alpha(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2n_alpha_pool_mask(const float* alpha_zyx, int gx, int gy, int gz, float thres, float* mask, int32_t* bbox8,
+                        t2n_stream_t stream) {
+    if (!alpha_zyx || !mask || !bbox8 || gx <= 0 || gy <= 0 || gz <= 0) return T2N_E_BADARG;
+    PoolMaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.alpha_zyx = alpha_zyx; a.gx = gx; a.gy = gy; a.gz = gz; a.thres = thres; a.mask = mask; a.bbox = bbox8;
+    return launch_pool_mask(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2n_filter_rays(const T2NField* field, const T2NAlphaMask* mask, const float* rays, long long n, int n_samples,
+                    int bbox_only, unsigned char* keep, t2n_stream_t stream) {
+    if (!field || !rays || !keep || n <= 0) return T2N_E_BADARG;
+    if (!bbox_only && (!mask || !mask->volume || n_samples <= 0)) return T2N_E_BADARG;
+    FilterRaysArgs a;
+    memset(&a, 0, sizeof(a));
+    a.f = make_field_dev(field, mask);
+    a.rays = rays; a.n = n; a.n_samples = n_samples; a.bbox_only = bbox_only; a.keep = keep;
+    return launch_filter_rays(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int resample_args(const float* src, int H, int W, int C, float* dst, int H2, int W2, ResampleArgs& a) {
+    if (!src || !dst || H <= 0 || W <= 0 || C <= 0 || H2 <= 0 || W2 <= 0) return T2N_E_BADARG;
+    if ((C & 3) || !aligned16(src) || !aligned16(dst)) return T2N_E_LAYOUT;
+    memset(&a, 0, sizeof(a));
+    a.src = src; a.H = H; a.W = W; a.C = C; a.dst = dst; a.H2 = H2; a.W2 = W2;
+    return 0;
+}
+
+int t2n_resample_plane(const float* src, int H, int W, int C, float* dst, int H2, int W2, t2n_stream_t stream) {
+    ResampleArgs a;
+    const int rc = resample_args(src, H, W, C, dst, H2, W2, a);
+    if (rc) return rc;
+    return launch_resample_plane(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2n_crop_plane(const float* src, int H, int W, int C, int y0, int x0, float* dst, int H2, int W2,
+                   t2n_stream_t stream) {
+    ResampleArgs a;
+    const int rc = resample_args(src, H, W, C, dst, H2, W2, a);
+    if (rc) return rc;
+    if (y0 < 0 || x0 < 0 || y0 + H2 > H || x0 + W2 > W) return T2N_E_BADARG;
+    a.y0 = y0; a.x0 = x0;
+    return launch_crop_plane(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -195,15 +195,48 @@ class TensorVMSplit(TensorBase):
         return self.basis_mat((pv * lv).T)
 
     # ---- grid maintenance (tensoRF.py:243-303) -----------------------------------------------------
+    # CUDA-resident factors are resampled / cropped by kernels that read and write the texel-major layout directly
+    # (csrc/maint.cu: no NCHW round trip, one launch per factor).  Factors that live on the host (checkpoint surgery,
+    # host-logic tests) are reshaped with tensor ops; which one runs is decided by where the data is, never by whether
+    # the library happens to be loadable.
+    @staticmethod
+    def _resample(t, H2, W2):
+        """F.interpolate(t, size=(H2, W2), mode='bilinear', align_corners=True) of a [1,C,H,W] factor, channels-last."""
+        if not t.is_cuda:
+            return F.interpolate(t, size=(H2, W2), mode='bilinear', align_corners=True).contiguous(memory_format=_CL)
+        lib = nat.load()
+        src = _texel_major(t.detach())
+        _, C_, H, W = src.shape
+        dst = torch.empty((1, C_, H2, W2), device=t.device, dtype=torch.float32).contiguous(memory_format=_CL)
+        with torch.cuda.device(t.device):
+            rc = lib.t2n_resample_plane(src.data_ptr(), H, W, C_, dst.data_ptr(), H2, W2,
+                                        torch.cuda.current_stream(t.device).cuda_stream)
+        nat.check(rc, "t2n_resample_plane")
+        return dst
+
+    @staticmethod
+    def _crop(t, y0, y1, x0, x1):
+        """t[..., y0:y1, x0:x1] of a [1,C,H,W] factor as a new channels-last tensor."""
+        if not t.is_cuda:
+            return t[..., y0:y1, x0:x1].contiguous(memory_format=_CL)
+        lib = nat.load()
+        src = _texel_major(t.detach())
+        _, C_, H, W = src.shape
+        H2, W2 = y1 - y0, x1 - x0
+        dst = torch.empty((1, C_, H2, W2), device=t.device, dtype=torch.float32).contiguous(memory_format=_CL)
+        with torch.cuda.device(t.device):
+            rc = lib.t2n_crop_plane(src.data_ptr(), H, W, C_, y0, x0, dst.data_ptr(), H2, W2,
+                                    torch.cuda.current_stream(t.device).cuda_stream)
+        nat.check(rc, "t2n_crop_plane")
+        return dst
+
     @torch.no_grad()
     def up_sampling_VM(self, plane_coef, line_coef, res_target):
         for i in range(3):
             a0, a1 = self.matMode[i]
             v = self.vecMode[i]
-            p = F.interpolate(plane_coef[i].data, size=(res_target[a1], res_target[a0]), mode='bilinear', align_corners=True)
-            l = F.interpolate(line_coef[i].data, size=(res_target[v], 1), mode='bilinear', align_corners=True)
-            plane_coef[i] = torch.nn.Parameter(p.contiguous(memory_format=_CL))
-            line_coef[i] = torch.nn.Parameter(l.contiguous(memory_format=_CL))
+            plane_coef[i] = torch.nn.Parameter(self._resample(plane_coef[i].data, int(res_target[a1]), int(res_target[a0])))
+            line_coef[i] = torch.nn.Parameter(self._resample(line_coef[i].data, int(res_target[v]), 1))
         return plane_coef, line_coef
 
     @torch.no_grad()
@@ -222,14 +255,14 @@ class TensorVMSplit(TensorBase):
         hi = (xyz_max - self.aabb[0]) / self.units
         lo, hi = torch.round(torch.round(lo)).long(), torch.round(hi).long() + 1
         hi = torch.stack([hi, self.gridSize]).amin(0)
+        lo_h, hi_h = [int(v) for v in lo.tolist()], [int(v) for v in hi.tolist()]     # one host read of the six bounds
         for i in range(3):
             v = self.vecMode[i]
             a0, a1 = self.matMode[i]
             for lines in (self.density_line, self.app_line):
-                lines[i] = torch.nn.Parameter(lines[i].data[..., lo[v]:hi[v], :].contiguous(memory_format=_CL))
+                lines[i] = torch.nn.Parameter(self._crop(lines[i].data, lo_h[v], hi_h[v], 0, 1))
             for planes in (self.density_plane, self.app_plane):
-                planes[i] = torch.nn.Parameter(
-                    planes[i].data[..., lo[a1]:hi[a1], lo[a0]:hi[a0]].contiguous(memory_format=_CL))
+                planes[i] = torch.nn.Parameter(self._crop(planes[i].data, lo_h[a1], hi_h[a1], lo_h[a0], hi_h[a0]))
         if not torch.all(self.alphaMask.gridSize == self.gridSize):
             t_lo, t_hi = lo / (self.gridSize - 1), (hi - 1) / (self.gridSize - 1)
             fixed = torch.zeros_like(new_aabb)
@@ -237,9 +270,8 @@ class TensorVMSplit(TensorBase):
             fixed[1] = (1 - t_hi) * self.aabb[0] + t_hi * self.aabb[1]
             print("aabb", new_aabb, "\ncorrect aabb", fixed)
             new_aabb = fixed
-        new_size = hi - lo
         self.aabb = new_aabb
-        self.update_stepSize((int(new_size[0]), int(new_size[1]), int(new_size[2])))
+        self.update_stepSize((hi_h[0] - lo_h[0], hi_h[1] - lo_h[1], hi_h[2] - lo_h[2]))
         self._refresh_flat_grads()
 
     # ---- native glue -------------------------------------------------------------------------------

@@ -601,49 +601,94 @@ class TensorBase(torch.nn.Module):
         pass
 
     # ---- alpha-mask maintenance (tensorBase.py:328-404) ----------------------------------------
+    # On a CUDA-resident model every step is a kernel of libt2n_b200.so (csrc/maint.cu): the dense alpha grid is ONE
+    # launch (the reference loops over gridSize[0] slabs of compute_alpha), the mask update two more.  A module whose
+    # tensors live on the host (checkpoint surgery, host-logic tests) has no alpha kernels: compute_alpha raises there.
+    def _dense_alpha_native(self, gridSize, want_xyz_layout=True, want_zyx=False, want_xyz=True):
+        lib = nat.load()
+        gx, gy, gz = [int(g) for g in gridSize]
+        dev = self.aabb.device
+        # torch.linspace on the host, like the reference (tensorBase.py:332-336), then moved to the device
+        sx, sy, sz = [torch.linspace(0, 1, g).to(dev) for g in (gx, gy, gz)]
+        f32 = dict(device=dev, dtype=torch.float32)
+        alpha_xyz = torch.empty((gx, gy, gz), **f32) if want_xyz_layout else None
+        alpha_zyx = torch.empty((gz, gy, gx), **f32) if want_zyx else None
+        xyz = torch.empty((gx, gy, gz, 3), **f32) if want_xyz else None
+        p_cl = self._native_param_tensors(self._flat_params())
+        field, pstruct = self._native_field(), self._native_params(p_cl)
+        mask = self.alphaMask.native() if self.alphaMask is not None else None
+        with torch.cuda.device(dev):
+            rc = lib.t2n_dense_alpha(C.byref(field), C.byref(pstruct), C.byref(mask) if mask else None,
+                                     sx.data_ptr(), sy.data_ptr(), sz.data_ptr(), gx, gy, gz, float(self.stepSize),
+                                     _ptr(alpha_xyz), _ptr(alpha_zyx), _ptr(xyz), torch.cuda.current_stream(dev).cuda_stream)
+        nat.check(rc, "t2n_dense_alpha")
+        return alpha_xyz, alpha_zyx, xyz, (sx, sy, sz)
+
     @torch.no_grad()
     def getDenseAlpha(self, gridSize=None):
         gridSize = self.gridSize if gridSize is None else gridSize
-        gx, gy, gz = [int(g) for g in gridSize]
-        lin = [torch.linspace(0, 1, g) for g in (gx, gy, gz)]
-        samples = torch.stack(torch.meshgrid(*lin, indexing="ij"), -1).to(self.device)
-        dense_xyz = self.aabb[0] * (1 - samples) + self.aabb[1] * samples
-        alpha = self.compute_alpha(dense_xyz.view(-1, 3), self.stepSize).view(gx, gy, gz)
+        if not self.aabb.is_cuda:
+            raise nat.NativeLibraryError("getDenseAlpha needs the model on a CUDA device (no CPU path)")
+        alpha, _, dense_xyz, _ = self._dense_alpha_native(gridSize)
         return alpha, dense_xyz
 
     @torch.no_grad()
     def updateAlphaMask(self, gridSize=(200, 200, 200)):
-        alpha, dense_xyz = self.getDenseAlpha(gridSize)
-        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
-        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
-        total_voxels = gridSize[0] * gridSize[1] * gridSize[2]
-        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gridSize[::-1])
-        alpha = (alpha >= self.alphaMask_thres).float()
-        self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
-        occupied = dense_xyz[alpha > 0.5]
-        xyz_min, xyz_max = occupied.amin(0), occupied.amax(0)
-        print(f"bbox: {xyz_min, xyz_max} alpha rest %%%f" % (torch.sum(alpha) / total_voxels * 100))
+        if not self.aabb.is_cuda:
+            raise nat.NativeLibraryError("updateAlphaMask needs the model on a CUDA device (no CPU path)")
+        lib = nat.load()
+        gx, gy, gz = [int(g) for g in gridSize]
+        dev = self.aabb.device
+        _, alpha_zyx, _, lin = self._dense_alpha_native(gridSize, want_xyz_layout=False, want_zyx=True, want_xyz=False)
+        volume = torch.empty((gz, gy, gx), device=dev, dtype=torch.float32)
+        bbox = torch.empty((8,), device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            rc = lib.t2n_alpha_pool_mask(alpha_zyx.data_ptr(), gx, gy, gz, float(self.alphaMask_thres), volume.data_ptr(),
+                                         bbox.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        nat.check(rc, "t2n_alpha_pool_mask")
+        self.alphaMask = AlphaGridMask(self.device, self.aabb, volume)
+        b = bbox.tolist()                       # the one device->host read of the update (the caller prints the box)
+        if b[6] == 0:
+            raise RuntimeError("updateAlphaMask: no voxel passes alphaMask_thres (the reference fails on the empty amin too)")
+        # occupied bbox = voxel positions at the extreme indices (positions are monotone in the index on every axis):
+        # aabb[0] * (1 - s) + aabb[1] * s evaluated like getDenseAlpha evaluates it
+        lo_s = torch.stack([lin[a][b[a]] for a in range(3)])
+        hi_s = torch.stack([lin[a][b[3 + a]] for a in range(3)])
+        xyz_min = self.aabb[0] * (1 - lo_s) + self.aabb[1] * lo_s
+        xyz_max = self.aabb[0] * (1 - hi_s) + self.aabb[1] * hi_s
+        total_voxels = gx * gy * gz
+        print(f"bbox: {xyz_min, xyz_max} alpha rest %%%f" % (b[6] / total_voxels * 100))
         return torch.stack((xyz_min, xyz_max))
 
     @torch.no_grad()
     def filtering_rays(self, all_rays, all_rgbs, all_depth=None, N_samples=256, chunk=10240 * 5, bbox_only=False):
+        """tensorBase.py:372-404.  One kernel per chunk of rays (thread per ray; the alpha mode marches the ray's
+        evaluation samples through the occupancy volume with early exit) instead of materialising [chunk, N, 3] points.
+        Chunks are as large as the caller allows: rays stay on the host, only the chunk and its 1-byte mask cross."""
         print('========> filtering rays ...')
         tt = time.time()
-        N = torch.tensor(all_rays.shape[:-1]).prod()
-        keep = []
-        for idx in torch.split(torch.arange(N), chunk):
-            rays = all_rays[idx].to(self.device)
-            o, d = rays[..., :3], rays[..., 3:6]
-            if bbox_only:
-                safe_d = torch.where(d == 0, torch.full_like(d, 1e-6), d)
-                t_hi = (self.aabb[1] - o) / safe_d
-                t_lo = (self.aabb[0] - o) / safe_d
-                hit = torch.maximum(t_hi, t_lo).amin(-1) > torch.minimum(t_hi, t_lo).amax(-1)
-            else:
-                pts, _, _ = self.sample_ray(o, d, N_samples=N_samples, is_train=False)
-                hit = (self.alphaMask.sample_alpha(pts).view(pts.shape[:-1]) > 0).any(-1)
-            keep.append(hit.cpu())
-        keep = torch.cat(keep).view(all_rgbs.shape[:-1])
+        if not self.aabb.is_cuda:
+            raise nat.NativeLibraryError("filtering_rays needs the model on a CUDA device (no CPU path)")
+        if not bbox_only and self.alphaMask is None:
+            raise AttributeError("'NoneType' object has no attribute 'sample_alpha'")       # what the reference raises
+        lib = nat.load()
+        dev = self.aabb.device
+        flat = all_rays.reshape(-1, all_rays.shape[-1])
+        N = flat.shape[0]
+        field = self._native_field()
+        mask = None if bbox_only else self.alphaMask.native()
+        chunk = max(int(chunk), 1 << 20)
+        keep_parts = []
+        for s in range(0, N, chunk):
+            rays = flat[s:s + chunk, :6].to(dev, torch.float32, non_blocking=True).contiguous()
+            keep = torch.empty((rays.shape[0],), device=dev, dtype=torch.uint8)
+            with torch.cuda.device(dev):
+                rc = lib.t2n_filter_rays(C.byref(field), C.byref(mask) if mask else None, rays.data_ptr(), rays.shape[0],
+                                         int(N_samples), int(bool(bbox_only)), keep.data_ptr(),
+                                         torch.cuda.current_stream(dev).cuda_stream)
+            nat.check(rc, "t2n_filter_rays")
+            keep_parts.append(keep)
+        keep = torch.cat(keep_parts).bool().to(all_rays.device).view(all_rgbs.shape[:-1])
         print(f'Ray filtering done! takes {time.time()-tt} s. ray mask ratio: {torch.sum(keep) / N}')
         if all_depth is not None:
             return all_rays[keep], all_rgbs[keep], all_depth[keep]

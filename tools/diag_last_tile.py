@@ -12,7 +12,7 @@ spec = orc.FieldSpec(aabb=[[-1.5, -1.5, 2.5], [1.5, 1.5, 5.5]], grid=[300, 300, 
 params = orc.init_params(spec, seed=0, density_gain=10.8, app_gain=1.0)
 S = orc.derive_step(spec)[1]
 model = build_model(spec, params, dev)
-for R in (64, 128, 256, 512, 1024, 3000):
+for R in [int(x) for x in os.environ.get("RS", "64,128,256,512,1024,3000").split(",")]:
     g = torch.Generator().manual_seed(9)
     px = torch.rand(R, 2, generator=g) * 800.0
     d = torch.cat([(px - 400.0) / 1111.1, torch.ones(R, 1)], -1)
