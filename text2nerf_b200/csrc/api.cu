@@ -625,17 +625,12 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
             line_bytes += field->grid[2 - i] * field->n_sigma[i] * 4;
         }
         a.rays = batch->rays; a.R = batch->R; a.S = batch->S; a.white_bg = batch->white_bg;
-        a.lines_in_smem = line_bytes <= 96 * 1024;
-        if (!a.lines_in_smem) line_bytes = 0;
         a.z_vals = out->z_vals; a.weight = out->weight; a.sigma_feat = scratch->sigma_feat; a.trans = scratch->trans;
         a.ray_start = scratch->ray_start; a.ray_count = scratch->ray_count; a.ray_flags = scratch->ray_flags;
         a.app_rgb = scratch->app_rgb; a.g_rgb = g_rgb_map; a.g_depth = g_depth_map; a.g_weight = g_weight;
         if (trans_grad) { a.gw_coef = trans_grad->coef; a.depth_gt = trans_grad->depth_gt; a.delta = trans_grad->delta; }
-        int ctas_per_sm = line_bytes > 0 ? (int)((220 * 1024) / (line_bytes + 1024)) : 4;
-        ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
-        int grid = dev.sm_count * ctas_per_sm;
-        const int need = (batch->R + 7) / 8;
-        if (grid > need) grid = need;
+        line_bytes = 0;
+        const int grid = (batch->R + 3) / 4;
         g_prof.start(6, st);
         rc = launch_ray_backward(a, max_quads(field->n_sigma), line_bytes, grid, st);
         g_prof.stop(st);

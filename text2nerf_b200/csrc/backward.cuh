@@ -10,6 +10,7 @@
 //                         reduce weight gradients (thread-owned registers for the small ones,
 //                         vector red.global for W1/W2), scatter into the app planes/lines.
 #pragma once
+#include <climits>
 #include "common.cuh"
 #include "march.cuh"
 #include "appearance.cuh"
@@ -29,7 +30,6 @@ struct RayBwdArgs {
     const float* rays;
     int R, S;
     int white_bg;
-    int lines_in_smem;          // gradient accumulators for the lines live in shared memory
     const float* z_vals;
     const float* weight;
     const float* sigma_feat;
@@ -48,117 +48,100 @@ struct RayBwdArgs {
     float delta;
 };
 
-__device__ __forceinline__ void red_add_smem(float* p, float v) {
-    asm volatile("red.shared.add.f32 [%0], %1;" :: "r"(smem_u32(p)), "f"(v) : "memory");
-}
-
-// Sum float4 values over runs of lane groups (grp = lane >> 2, 8 groups of 4 channel lanes) that carry the same key.
-// The 8 groups hold consecutive samples of one ray; a shuffle-down doubling scan restricted to runs (no run start
-// between the two groups) leaves each run's total in its first group.
-__device__ __forceinline__ void seg_reduce_groups(unsigned heads, int grp, float4& va, float4& vb) {
-    // heads: ballot of "this group starts a run"; group g may absorb group g+off only if no run starts in (g, g+off]
-    const unsigned after = grp < 7 ? heads >> (4 * (grp + 1)) : 0u;
-#pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
-        float4 a2, b2;
-        a2.x = __shfl_down_sync(T2N_FULL, va.x, 4 * off); a2.y = __shfl_down_sync(T2N_FULL, va.y, 4 * off);
-        a2.z = __shfl_down_sync(T2N_FULL, va.z, 4 * off); a2.w = __shfl_down_sync(T2N_FULL, va.w, 4 * off);
-        b2.x = __shfl_down_sync(T2N_FULL, vb.x, 4 * off); b2.y = __shfl_down_sync(T2N_FULL, vb.y, 4 * off);
-        b2.z = __shfl_down_sync(T2N_FULL, vb.z, 4 * off); b2.w = __shfl_down_sync(T2N_FULL, vb.w, 4 * off);
-        if (grp + off < 8 && (after & ((1u << (4 * off)) - 1u)) == 0u) {
-            va.x += a2.x; va.y += a2.y; va.z += a2.z; va.w += a2.w;
-            vb.x += b2.x; vb.y += b2.y; vb.z += b2.z; vb.w += b2.w;
-        }
-    }
-}
-
-// Scatter of one step: every lane of the warp calls this (shuffles inside); `active` lanes own a sample with a
-// non-zero density-feature gradient df.  Plane texels get red.global.add.v4; the line gradients of the 8 samples
-// are first summed over runs of samples that hit the same line texels (neighbouring samples along a ray move a
-// fraction of a texel, the slow axes not at all), then only the run heads touch the accumulators -- the
-// shared-memory float atomic is a CAS loop (ATOMS.CAST.SPIN) that serialises on every same-address conflict.
+// Density scatter of one 32-sample pass (grid_sampler_2d_backward of compute_densityfeature, tensoRF.py:205-220): a
+// RUN-MERGING WALK.  Consecutive samples of a ray move a fraction of a voxel (half a voxel at step_ratio 0.5), so runs of
+// them share the bilinear cell of a plane and the two taps of a line.  Each half-warp walks 16 consecutive samples of
+// the pass IN ORDER; lane l of the half owns (plane l / 4, channel quad l % 4) [lanes 12..15 idle] and keeps, in
+// registers, the four texels of the plane cell and the two line taps it is currently in together with their gradient
+// accumulators.  Texels are (re)loaded and accumulators flushed (red.global.add.v4) only when the sample enters another
+// cell / line segment: loads and reds both drop by the run length.  The line gradients take the same route: after run
+// merging they are ~1 red.v4 per sample and lane, and same-address reds pipeline in the L2 (B300_MICROARCH: 0.85
+// cycles per lane-op on one address), so the per-CTA shared-memory accumulators of the previous version -- whose float
+// add is a CAS loop (ATOMS.CAST.SPIN, ~12 instructions per scalar) -- and their zero / flush passes are gone.
 template <int NQ>
-__device__ __forceinline__ void sigma_scatter(const RayBwdArgs& a, float* const* gl, const Axis ax[3], int c4, int grp,
-                                              bool active, float df) {
+__device__ __forceinline__ void sigma_scatter_walk(const RayBwdArgs& a, const SampleGeom& g, float df, unsigned nz, int lane) {
+    const int hf = lane >> 4, l = lane & 15, c4 = l & 3;
+    const bool worker = l < 12;
+    const int i = worker ? (l >> 2) : 0;
+    const int a0 = (i == 2) ? 1 : 0, a1 = (i == 0) ? 1 : 2, v = 2 - i;
+    const int C = a.sc[i], W = a.f.G[a0], GH = a.f.G[a1], GV = a.f.G[v];
+    const unsigned mine = (nz >> (16 * hf)) & 0xffffu;
+    const unsigned both = (nz | (nz >> 16)) & 0xffffu;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int a0 = (i == 2) ? 1 : 0;
-        const int a1 = (i == 0) ? 1 : 2;
-        const int v = 2 - i;
-        const int C = a.sc[i];
-        const int W = a.f.G[a0];
-        const Axis& X = ax[a0];
-        const Axis& Y = ax[a1];
-        const Axis& Z = ax[v];
-        const float nw = __fmul_rn(X.w0, Y.w0), ne = __fmul_rn(X.w1, Y.w0);
-        const float sw = __fmul_rn(X.w0, Y.w1), se = __fmul_rn(X.w1, Y.w1);
-        const float* P = a.sp[i];
-        const float* L = a.sl[i];
-        float* GP = a.gsp[i];
-        const size_t o00 = ((size_t)Y.c0 * W + X.c0) * C, o01 = ((size_t)Y.c0 * W + X.c1) * C;
-        const size_t o10 = ((size_t)Y.c1 * W + X.c0) * C, o11 = ((size_t)Y.c1 * W + X.c1) * C;
-        const int key = active ? (Z.c0 | (Z.c1 << 16)) : (-1 - grp);
-        const int key_prev = __shfl_up_sync(T2N_FULL, key, 4);
-        const bool starts = grp == 0 || key_prev != key;        // inactive groups carry unique keys: runs never span them
-        const unsigned heads = __ballot_sync(T2N_FULL, starts);
-        const bool head = active && starts;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int ch = (q * 4 + c4) * 4;
-            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-            if (active && ch < C) {
-                float4 t00 = ldg4(P + o00 + ch), t01 = ldg4(P + o01 + ch);
-                float4 t10 = ldg4(P + o10 + ch), t11 = ldg4(P + o11 + ch);
-                float4 l0 = ldg4(L + Z.c0 * C + ch), l1 = ldg4(L + Z.c1 * C + ch);
-                float4 pv = f4_fma(se, t11, f4_fma(sw, t10, f4_fma(ne, t01, f4_scale(nw, t00))));
-                float4 lv = f4_fma(Z.w1, l1, f4_scale(Z.w0, l0));
-                float4 dpl = f4_scale(df, lv);          // d/d(plane value)
-                float4 dln = f4_scale(df, pv);          // d/d(line value)
-                if (nw != 0.f) red_add_v4(GP + o00 + ch, f4_scale(nw, dpl));
-                if (ne != 0.f) red_add_v4(GP + o01 + ch, f4_scale(ne, dpl));
-                if (sw != 0.f) red_add_v4(GP + o10 + ch, f4_scale(sw, dpl));
-                if (se != 0.f) red_add_v4(GP + o11 + ch, f4_scale(se, dpl));
-                va = f4_scale(Z.w0, dln);
-                vb = f4_scale(Z.w1, dln);
-            }
-            seg_reduce_groups(heads, grp, va, vb);
-            if (head && ch < C) {
-                float* g0 = gl[i] + Z.c0 * C + ch;
-                float* g1 = gl[i] + Z.c1 * C + ch;
-                if (a.lines_in_smem) {
-                    if (va.x != 0.f) red_add_smem(g0, va.x);
-                    if (va.y != 0.f) red_add_smem(g0 + 1, va.y);
-                    if (va.z != 0.f) red_add_smem(g0 + 2, va.z);
-                    if (va.w != 0.f) red_add_smem(g0 + 3, va.w);
-                    if (vb.x != 0.f) red_add_smem(g1, vb.x);
-                    if (vb.y != 0.f) red_add_smem(g1 + 1, vb.y);
-                    if (vb.z != 0.f) red_add_smem(g1 + 2, vb.z);
-                    if (vb.w != 0.f) red_add_smem(g1 + 3, vb.w);
-                } else {
-                    red_add_v4(g0, va);
-                    red_add_v4(g1, vb);
+    for (int q = 0; q < NQ; ++q) {
+        const int ch = (q * 4 + c4) * 4;
+        const bool chan_ok = worker && ch < C;
+        const float* __restrict__ P = a.sp[i] + ch;
+        const float* __restrict__ L = a.sl[i] + ch;
+        float* GP = a.gsp[i] + ch;
+        float* GL = a.gsl[i] + ch;
+        int cx = INT_MIN, cy = INT_MIN, cz = INT_MIN;           // cell / segment the cached texels belong to
+        int o00 = 0, o01 = 0, o10 = 0, o11 = 0, lo0 = 0, lo1 = 0;
+        float4 t00 = zero4, t01 = zero4, t10 = zero4, t11 = zero4, l0 = zero4, l1 = zero4;
+        float4 g00 = zero4, g01 = zero4, g10 = zero4, g11 = zero4, gl0 = zero4, gl1 = zero4;
+        for (int j = 0; j < 16; ++j) {
+            if (!((both >> j) & 1u)) continue;                  // warp-uniform: neither half has a sample here
+            const int src = 16 * hf + j;
+            const int ix = __shfl_sync(T2N_FULL, g.i0[0], src), iy = __shfl_sync(T2N_FULL, g.i0[1], src);
+            const int iz = __shfl_sync(T2N_FULL, g.i0[2], src);
+            const float fx = __shfl_sync(T2N_FULL, g.fr[0], src), fy = __shfl_sync(T2N_FULL, g.fr[1], src);
+            const float fz = __shfl_sync(T2N_FULL, g.fr[2], src);
+            const float dfs = __shfl_sync(T2N_FULL, df, src);
+            if (!(chan_ok && ((mine >> j) & 1u))) continue;
+            // register selects of this lane's plane axes (a0, a1) and line axis v
+            const int xi = (a0 == 1) ? iy : ix, yi = (a1 == 1) ? iy : iz, zi = (v == 2) ? iz : ((v == 1) ? iy : ix);
+            const float xf = (a0 == 1) ? fy : fx, yf = (a1 == 1) ? fy : fz, zf = (v == 2) ? fz : ((v == 1) ? fy : fx);
+            if (xi != cx || yi != cy) {
+                if (cx != INT_MIN) {        // leave the cell: one red per corner (a zero-weight corner adds zeros)
+                    red_add_v4(GP + o00, g00); red_add_v4(GP + o01, g01);
+                    red_add_v4(GP + o10, g10); red_add_v4(GP + o11, g11);
+                    g00 = zero4; g01 = zero4; g10 = zero4; g11 = zero4;
                 }
+                cx = xi; cy = yi;
+                const int x0 = min(max(xi, 0), W - 1), x1 = min(max(xi + 1, 0), W - 1);
+                const int y0 = min(max(yi, 0), GH - 1), y1 = min(max(yi + 1, 0), GH - 1);
+                o00 = (y0 * W + x0) * C; o01 = (y0 * W + x1) * C;
+                o10 = (y1 * W + x0) * C; o11 = (y1 * W + x1) * C;
+                t00 = ldg4(P + o00); t01 = ldg4(P + o01);
+                t10 = ldg4(P + o10); t11 = ldg4(P + o11);
             }
+            if (zi != cz) {
+                if (cz != INT_MIN) {
+                    red_add_v4(GL + lo0, gl0); red_add_v4(GL + lo1, gl1);
+                    gl0 = zero4; gl1 = zero4;
+                }
+                cz = zi;
+                lo0 = min(max(zi, 0), GV - 1) * C; lo1 = min(max(zi + 1, 0), GV - 1) * C;
+                l0 = ldg4(L + lo0); l1 = ldg4(L + lo1);
+            }
+            // bilinear weights with the zeros-padding test folded in (make_axis): out-of-range taps get weight 0
+            const float xw0 = (xi >= 0 && xi < W) ? __fsub_rn(1.0f, xf) : 0.f, xw1 = (xi + 1 >= 0 && xi + 1 < W) ? xf : 0.f;
+            const float yw0 = (yi >= 0 && yi < GH) ? __fsub_rn(1.0f, yf) : 0.f, yw1 = (yi + 1 >= 0 && yi + 1 < GH) ? yf : 0.f;
+            const float zw0 = (zi >= 0 && zi < GV) ? __fsub_rn(1.0f, zf) : 0.f, zw1 = (zi + 1 >= 0 && zi + 1 < GV) ? zf : 0.f;
+            const float nw = __fmul_rn(xw0, yw0), ne = __fmul_rn(xw1, yw0);
+            const float sw = __fmul_rn(xw0, yw1), se = __fmul_rn(xw1, yw1);
+            const float4 pv = f4_fma(se, t11, f4_fma(sw, t10, f4_fma(ne, t01, f4_scale(nw, t00))));
+            const float4 lv = f4_fma(zw1, l1, f4_scale(zw0, l0));
+            const float4 dpl = f4_scale(dfs, lv);          // d/d(plane value)
+            const float4 dln = f4_scale(dfs, pv);          // d/d(line value)
+            g00 = f4_fma(nw, dpl, g00); g01 = f4_fma(ne, dpl, g01);
+            g10 = f4_fma(sw, dpl, g10); g11 = f4_fma(se, dpl, g11);
+            gl0 = f4_fma(zw0, dln, gl0); gl1 = f4_fma(zw1, dln, gl1);
         }
+        if (cx != INT_MIN) {
+            red_add_v4(GP + o00, g00); red_add_v4(GP + o01, g01);
+            red_add_v4(GP + o10, g10); red_add_v4(GP + o11, g11);
+        }
+        if (cz != INT_MIN) { red_add_v4(GL + lo0, gl0); red_add_v4(GL + lo1, gl1); }
     }
 }
 
 template <int NQ>
-__global__ void __launch_bounds__(256) ray_backward_kernel(const __grid_constant__ RayBwdArgs a) {
-    extern __shared__ __align__(16) float sm_gl[];
+__global__ void __launch_bounds__(128, 4) ray_backward_kernel(const __grid_constant__ RayBwdArgs a) {
     const FieldDev& f = a.f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    const int c4 = lane & 3, grp = lane >> 2;
     const int S = a.S;
-
-    float* gl[3] = {a.gsl[0], a.gsl[1], a.gsl[2]};
-    int line_elems = 0;
-    if (a.lines_in_smem) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { gl[i] = sm_gl + line_elems; line_elems += f.G[2 - i] * a.sc[i]; }
-        for (int i = threadIdx.x; i < line_elems; i += blockDim.x) sm_gl[i] = 0.f;
-        __syncthreads();
-    }
 
     for (int r = blockIdx.x * wpc + warp; r < a.R; r += gridDim.x * wpc) {
         const size_t row = (size_t)r * S;
@@ -232,38 +215,11 @@ __global__ void __launch_bounds__(256) ray_backward_kernel(const __grid_constant
                 float p[3];
                 sample_point(rs, z, p);
                 const SampleGeom g = sample_geom(f, p);
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const unsigned sub = (nz >> (8 * s)) & 0xffu;
-                    if (sub == 0) continue;
-                    const int src = 8 * s + grp;
-                    Axis ax[3];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        int i0 = __shfl_sync(T2N_FULL, g.i0[q], src);
-                        float fr = __shfl_sync(T2N_FULL, g.fr[q], src);
-                        ax[q] = make_axis(i0, fr, f.G[q]);
-                    }
-                    const float dfs = __shfl_sync(T2N_FULL, df, src);
-                    sigma_scatter<NQ>(a, gl, ax, c4, grp, ((sub >> grp) & 1u) != 0, dfs);
-                }
+                sigma_scatter_walk<NQ>(a, g, df, nz, lane);
             }
         }
     }
 
-    if (a.lines_in_smem) {
-        __syncthreads();
-        int off = 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int n = f.G[2 - i] * a.sc[i];
-            for (int j = threadIdx.x * 4; j < n; j += blockDim.x * 4) {
-                float4 v = lds4(sm_gl + off + j);
-                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(a.gsl[i] + j, v);
-            }
-            off += n;
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,13 +1,12 @@
 // ray sweep backward + fused data loss launchers
 #include "launch.h"
 namespace t2n {
+// one warp per ray, four rays per CTA, no state shared inside a CTA: the block scheduler balances rays of different
+// lengths (a persistent grid left the SMs that drew short rays idle)
 template <int NQ>
 static int go(const RayBwdArgs& a, int smem, int grid, cudaStream_t st) {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ray_backward_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    ray_backward_kernel<NQ><<<grid, 256, smem, st>>>(a);
+    (void)smem; (void)grid;
+    ray_backward_kernel<NQ><<<(a.R + 3) / 4, 128, 0, st>>>(a);
     return (int)cudaGetLastError();
 }
 int launch_ray_backward(const RayBwdArgs& a, int nq, int smem, int grid, cudaStream_t st) {
