@@ -176,7 +176,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
 
 
 KERNEL_NAMES = {0: "march", 1: "pack_w1", 2: "appearance", 3: "finalize", 4: "app_backward_ffma",
-                5: "unpack_w1_grad", 6: "ray_backward", 7: "pack_bwd", 8: "app_backward_mma", 9: "wgrad", 10: "data_loss", 11: "tv_sums", 12: "tv_grad", 13: "adam"}
+                5: "unpack_w1_grad", 6: "ray_backward", 7: "pack_bwd", 8: "app_backward_mma", 9: "wgrad", 10: "data_loss", 11: "tv_sums", 12: "tv_grad", 13: "adam", 14: "app_scatter"}
 
 
 def profile_read():

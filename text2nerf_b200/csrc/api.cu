@@ -540,7 +540,8 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
             d.dz1_img = img;  img += (size_t)cap_rows * 1024;
             d.dfeat_img = img; img += (size_t)cap_rows * 256;
             d.prod_img = img; img += (size_t)cap_rows * 256 * ngp;
-            d.dz3_img = img;
+            d.dz3_img = img;  img += (size_t)cap_rows * 256;
+            d.dprod = reinterpret_cast<float*>(img);
             for (int i = 0; i < 3; ++i) { d.gap[i] = b.gap[i]; d.gal[i] = b.gal[i]; }
             d.g_b3 = grads->b3;
             if (getenv("T2N_BWD_TRACE")) {
@@ -554,6 +555,17 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
             rc = launch_app_backward_mma(d, smem_bd, getenv("T2N_BWD_GRID") ? atoi(getenv("T2N_BWD_GRID")) : dev.sm_count, st);
             g_prof.stop(st);
             if (rc) return rc;
+            {   // gather + scatter of the listed samples (products image for dBasis, gradients of the app factors)
+                AppScatterArgs sa;
+                memset(&sa, 0, sizeof(sa));
+                sa.fw = b.fw; sa.dprod = d.dprod; sa.ld = 32 * ngp; sa.ngp = ngp; sa.cap_rows = cap_rows;
+                sa.prod_img = d.prod_img;
+                for (int i = 0; i < 3; ++i) { sa.gap[i] = b.gap[i]; sa.gal[i] = b.gal[i]; }
+                g_prof.start(14, st);
+                rc = launch_app_scatter(sa, dev.sm_count, st);
+                g_prof.stop(st);
+                if (rc) return rc;
+            }
 
             WgradArgs w;
             auto base = [&](const uint8_t* x, int ngx, const uint8_t* y, int ngy, float* o, float* ones) {

@@ -15,6 +15,11 @@ int launch_app_backward_mma(const BwdMmaArgs& a, int smem_bytes, int grid, cudaS
     kern<<<grid, kMmaThreads, smem_bytes, st>>>(a);
     return (int)cudaGetLastError();
 }
+int launch_app_scatter(const AppScatterArgs& a, int sm_count, cudaStream_t st) {
+    // the list length is only known on the device: a persistent grid of 4-warp CTAs strides over the 32-entry blocks
+    app_scatter_kernel<<<sm_count * 16, 128, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
 int launch_wgrad(WgradArgs& a, int max_smem, int grid, cudaStream_t st) {
     const int stage = wgrad_stage_bytes(a.ngx, a.ngy);
     int ns = (max_smem - kImgGroupBytes - 32 * 8 - 1024) / stage;

@@ -23,10 +23,12 @@
 //          entries
 //   P4  dfeat                                                      -> TMEM A, dfeat image
 //   M3  dprod
-//   P5  gather plane/line texels (8 channels per thread), products image, dprod from TMEM, red.v4 scatter
+//   P5  dprod from TMEM -> global [rows][32 * groups]; the gather of the plane/line texels, the products image and the
+//       scatter-add into the appearance factors run in app_scatter_kernel (scatter.cuh) behind this kernel
 #pragma once
 #include "bwd_mma_defs.cuh"
 #include "wgrad_mma.cuh"
+#include "scatter.cuh"
 
 namespace t2n {
 
@@ -272,7 +274,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
             uint8_t* dz2_t = args.dz2_img + (size_t)tile * img_tile_bytes(4);
             uint8_t* dz1_t = args.dz1_img + (size_t)tile * img_tile_bytes(4);
             uint8_t* dfeat_t = args.dfeat_img + (size_t)tile * img_tile_bytes(1);
-            uint8_t* prod_t = args.prod_img + (size_t)tile * img_tile_bytes(ngp);
             uint8_t* dz3_t = args.dz3_img + (size_t)tile * img_tile_bytes(1);
             const uint8_t* h1_t = args.h1_img + (size_t)tile * img_tile_bytes(4);
             const uint8_t* h2_t = args.h2_img + (size_t)tile * img_tile_bytes(4);
@@ -283,11 +284,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
             RaySetup rs;
 #pragma unroll
             for (int i = 0; i < 3; ++i) { rs.o[i] = 0.f; rs.d[i] = 0.f; }
-            float zs = 0.f;
             if (live) {
                 slot = __ldg(a.slots + e);
                 r = slot / a.S;
-                zs = __ldg(a.z_vals + slot);
                 const float* ray = a.rays + (size_t)r * 6;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { rs.o[i] = __ldg(ray + i); rs.d[i] = __ldg(ray + 3 + i); }
@@ -428,78 +427,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) app_backward_mma_kernel(const 
             publish_a();
             mark(4);
 
-            // ================= P5: gather, products image, dprod, scatter =================
-            Axis ax[3];
-            if (live) {
-                float p[3];
-                sample_point(rs, zs, p);
-                const SampleGeom sg = sample_geom(a.f, p);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) ax[i] = make_axis(sg.i0[i], sg.fr[i], a.f.G[i]);
-            }
+            // ================= P5: d loss / d product -> global (the gather + scatter is app_scatter_kernel, scatter.cuh) =====
+            mbar_wait(bar_acc + 1, t & 1);
+            tc_fence_after();
             for (int j = 0; j < ngp; ++j) {
-                const int comp0 = 32 * j + 8 * q;
-                float prod[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                float4 pv[2], lv[2];
-                size_t o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-                float nw = 0.f, ne = 0.f, sw = 0.f, se = 0.f, zw0 = 0.f, zw1 = 0.f;
-                int fi = 0, ch0 = 0, zc0 = 0, zc1 = 0, C = 0;
-                const bool on = live && comp0 < a.n_app_total;
-                if (on) {
-                    fi = comp0 >= a.aoff[2] ? 2 : (comp0 >= a.aoff[1] ? 1 : 0);
-                    ch0 = comp0 - a.aoff[fi];
-                    const int a0 = (fi == 2) ? 1 : 0, a1 = (fi == 0) ? 1 : 2, vv = 2 - fi;
-                    C = a.ac[fi];
-                    const int W = a.f.G[a0];
-                    // register selects (no dynamically indexed local array)
-                    const Axis X = (a0 == 1) ? ax[1] : ax[0];
-                    const Axis Y = (a1 == 1) ? ax[1] : ax[2];
-                    const Axis Z = (vv == 2) ? ax[2] : ((vv == 1) ? ax[1] : ax[0]);
-                    nw = __fmul_rn(X.w0, Y.w0); ne = __fmul_rn(X.w1, Y.w0);
-                    sw = __fmul_rn(X.w0, Y.w1); se = __fmul_rn(X.w1, Y.w1);
-                    zw0 = Z.w0; zw1 = Z.w1; zc0 = Z.c0; zc1 = Z.c1;
-                    o00 = ((size_t)Y.c0 * W + X.c0) * C; o01 = ((size_t)Y.c0 * W + X.c1) * C;
-                    o10 = ((size_t)Y.c1 * W + X.c0) * C; o11 = ((size_t)Y.c1 * W + X.c1) * C;
-                    const float* Pp = a.ap[fi] + ch0;
-                    const float* Lp = a.al[fi] + ch0;
-                    float4 t00[2], t01[2], t10[2], t11[2], l0[2], l1[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        t00[u] = ldg4(Pp + o00 + 4 * u); t01[u] = ldg4(Pp + o01 + 4 * u);
-                        t10[u] = ldg4(Pp + o10 + 4 * u); t11[u] = ldg4(Pp + o11 + 4 * u);
-                        l0[u] = ldg4(Lp + (size_t)zc0 * C + 4 * u); l1[u] = ldg4(Lp + (size_t)zc1 * C + 4 * u);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        pv[u] = f4_fma(se, t11[u], f4_fma(sw, t10[u], f4_fma(ne, t01[u], f4_scale(nw, t00[u]))));
-                        lv[u] = f4_fma(zw1, l1[u], f4_scale(zw0, l0[u]));
-                        const float4 pr = f4_mul(pv[u], lv[u]);
-                        prod[4 * u] = pr.x; prod[4 * u + 1] = pr.y; prod[4 * u + 2] = pr.z; prod[4 * u + 3] = pr.w;
-                    }
-                }
-                img_store8(prod_t, ngp, m, j, q, prod);
-                if (j == 0) {
-                    mbar_wait(bar_acc + 1, t & 1);
-                    tc_fence_after();
-                }
                 uint32_t dv[8];
-                tmem_ld8(tmem + tmem_lane + kBwdColDH1 + comp0, dv);
-                if (on) {
-                    float* GP = args.gap[fi] + ch0;
-                    float* GL = args.gal[fi] + ch0;
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float4 dp = make_float4(__uint_as_float(dv[4 * u]), __uint_as_float(dv[4 * u + 1]),
-                                                      __uint_as_float(dv[4 * u + 2]), __uint_as_float(dv[4 * u + 3]));
-                        const float4 dpl = f4_mul(dp, lv[u]);
-                        const float4 dln = f4_mul(dp, pv[u]);
-                        if (nw != 0.f) red_add_v4(GP + o00 + 4 * u, f4_scale(nw, dpl));
-                        if (ne != 0.f) red_add_v4(GP + o01 + 4 * u, f4_scale(ne, dpl));
-                        if (sw != 0.f) red_add_v4(GP + o10 + 4 * u, f4_scale(sw, dpl));
-                        if (se != 0.f) red_add_v4(GP + o11 + 4 * u, f4_scale(se, dpl));
-                        if (zw0 != 0.f) red_add_v4(GL + (size_t)zc0 * C + 4 * u, f4_scale(zw0, dln));
-                        if (zw1 != 0.f) red_add_v4(GL + (size_t)zc1 * C + 4 * u, f4_scale(zw1, dln));
-                    }
+                tmem_ld8(tmem + tmem_lane + kBwdColDH1 + 32 * j + 8 * q, dv);
+                if (live) {
+                    float4* dst = reinterpret_cast<float4*>(args.dprod + (size_t)e * (32 * ngp) + 32 * j + 8 * q);
+                    dst[0] = make_float4(__uint_as_float(dv[0]), __uint_as_float(dv[1]), __uint_as_float(dv[2]), __uint_as_float(dv[3]));
+                    dst[1] = make_float4(__uint_as_float(dv[4]), __uint_as_float(dv[5]), __uint_as_float(dv[6]), __uint_as_float(dv[7]));
                 }
             }
             tc_fence_before();      // TMEM reads of this tile are complete (tmem_ld8 waits) before the next tile's arrivals

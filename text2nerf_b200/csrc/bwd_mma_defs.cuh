@@ -79,7 +79,8 @@ __host__ __device__ inline int bwd_group_rows(int chunks, int g) {      // rows 
 // (dz2, dz1: 4 groups; dfeat, dz3: 1 group; products: ceil(NA/32) groups).  The decoder input columns (Kp/32
 // groups, the largest operand) are NOT materialised: the dW1 GEMM regenerates them from the saved features.
 __host__ __device__ inline size_t bwd_img_row_bytes(int n_app_total, int Kp) {
-    return (size_t)256 * (4 + 4 + 1 + 1 + (n_app_total + 31) / 32);
+    // + d loss / d product, plain fp32 [rows][32 * groups] (bwd_mma -> app_scatter)
+    return (size_t)256 * (4 + 4 + 1 + 1 + (n_app_total + 31) / 32) + (size_t)128 * ((n_app_total + 31) / 32);
 }
 
 constexpr int kBwdNB = 4;               // weight-chunk ring depth (32 KB stages)
@@ -123,6 +124,7 @@ struct BwdMmaArgs {
     long long cap_rows;
     // images written here
     uint8_t* dz2_img; uint8_t* dz1_img; uint8_t* dfeat_img; uint8_t* prod_img; uint8_t* dz3_img;
+    float* dprod;               // [rows][32 * b_chunks] d loss / d product (consumed by app_scatter_kernel)
     // gradients accumulated directly
     float* gap[3]; float* gal[3];
     float* g_b3;
@@ -135,6 +137,18 @@ struct BwdPackArgs {
     unsigned char own[32];
     short perm[32 * (1 + 2 * kMaxFreq)];
     float* out;
+};
+
+// ---- gather + scatter kernel behind the backward-data kernel (scatter.cuh)
+struct AppScatterArgs {
+    AppArgs fw;                 // field geometry, app factors, list (slots, z_vals, rays, counters)
+    const float* dprod;         // [rows][ld]  d loss / d (plane*line product), written by app_backward_mma_kernel
+    int ld;                     // 32 * ngp
+    int ngp;                    // 32-column groups of the product image
+    long long cap_rows;
+    uint8_t* prod_img;          // operand image of the products (dBasis GEMM), all rows of every started tile
+    float* gap[3];
+    float* gal[3];
 };
 
 // ---- weight-gradient GEMM kernel (wgrad_mma.cuh)

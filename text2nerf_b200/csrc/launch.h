@@ -24,6 +24,7 @@ int launch_unpack_w1_grad(const float* gw1p, const int32_t* perm, int C, int K, 
 int launch_pack_bwd(const BwdPackArgs& a, cudaStream_t st);
 int launch_app_backward_mma(const BwdMmaArgs& a, int smem_bytes, int grid, cudaStream_t st);
 int launch_wgrad(WgradArgs& a, int max_smem, int grid, cudaStream_t st);
+int launch_app_scatter(const AppScatterArgs& a, int sm_count, cudaStream_t st);
 int launch_tv_sums(const TvArgs& a, int grid, cudaStream_t st);
 int launch_tv_grad(const TvArgs& a, int grid, cudaStream_t st);
 int launch_adam(const AdamTable& a, cudaStream_t st);
