@@ -90,6 +90,7 @@ bool mma_recipe(const T2NField* f, MmaRecipe& R) {
     return build_mma_recipe(f->shading, f->app_dim, f->fea_pe, f->view_pe, R);
 }
 
+
 int max_quads(const int n[3]) {
     int m = n[0] > n[1] ? n[0] : n[1];
     m = m > n[2] ? m : n[2];
@@ -121,7 +122,62 @@ struct Profiler {
 };
 Profiler g_prof;
 long long* g_trace = nullptr;
+
+// Side streams of the backward pass (one set per device, created on first use; nothing is ever synchronised with the
+// host).  The backward forks after its inputs are ready and joins before it returns control of the caller's stream:
+//      caller's stream : weight images -> backward-data (tcgen05) -> dW2, dW1, dW3 GEMMs -> ............ join
+//      side 0          :                         (after backward-data) gather/scatter -> dBasis GEMM ----^
+//      side 1          : ray sweep + density scatter (needs forward state only) --------------------------^
+// The three branches use different resources (the weight-gradient GEMMs stream operand images from HBM through TMA
+// with 18 k registers per SM, the scatter kernels are latency-bound red / L2 traffic, the ray sweep is issue-bound), so
+// they co-reside on the SMs instead of queueing behind each other.  T2N_BWD_SERIAL=1 or enabled profiling (per-kernel
+// event times must not overlap) keeps everything on the caller's stream.
+struct SideStreams {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, mid = nullptr, join[2] = {nullptr, nullptr};
+    bool ok = false;
+};
+SideStreams& side_streams() {
+    static SideStreams all[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStreams& ss = all[dev & 63];
+    if (!ss.ok) {
+        bool good = true;
+        for (int i = 0; i < 2; ++i) {
+            good = good && cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) == cudaSuccess;
+            good = good && cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        good = good && cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&ss.mid, cudaEventDisableTiming) == cudaSuccess;
+        ss.ok = good;
+    }
+    return ss;
+}
 constexpr int kTraceLen = 8192;   // 64 counters + timeline events of the forward appearance kernel
+
+int max_quads(const int n[3]);
+int enqueue_ray_backward(const T2NField* field, const T2NParams* params, const FieldDev& fd, const T2NBatch* batch,
+                         const T2NOutputs* out, const T2NScratch* scratch, const float* g_rgb_map, const float* g_depth_map,
+                         const float* g_weight, const T2NTransGrad* trans_grad, const T2NGrads* grads, cudaStream_t st) {
+    RayBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.f = fd;
+    for (int i = 0; i < 3; ++i) {
+        a.sp[i] = params->sigma_plane[i]; a.sl[i] = params->sigma_line[i]; a.sc[i] = field->n_sigma[i];
+        a.gsp[i] = grads->sigma_plane[i]; a.gsl[i] = grads->sigma_line[i];
+        if (!a.gsp[i] || !a.gsl[i]) return T2N_E_BADARG;
+    }
+    a.rays = batch->rays; a.R = batch->R; a.S = batch->S; a.white_bg = batch->white_bg;
+    a.z_vals = out->z_vals; a.weight = out->weight; a.sigma_feat = scratch->sigma_feat; a.trans = scratch->trans;
+    a.ray_start = scratch->ray_start; a.ray_count = scratch->ray_count; a.ray_flags = scratch->ray_flags;
+    a.app_rgb = scratch->app_rgb; a.g_rgb = g_rgb_map; a.g_depth = g_depth_map; a.g_weight = g_weight;
+    if (trans_grad) { a.gw_coef = trans_grad->coef; a.depth_gt = trans_grad->depth_gt; a.delta = trans_grad->delta; }
+    g_prof.start(6, st);
+    const int rc = launch_ray_backward(a, max_quads(field->n_sigma), 0, (batch->R + 3) / 4, st);
+    g_prof.stop(st);
+    return rc;
+}
 
 AppArgs make_app_args(const T2NField* f, const T2NParams* p, const FieldDev& fd, const T2NBatch* b,
                       const T2NOutputs* out, const T2NScratch* s) {
@@ -474,7 +530,18 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const FieldDev fd = make_field_dev(field, mask);
     const bool mlp = field->shading <= T2N_SHADE_MLP;
-    // ---- appearance backward first (it only needs forward state), then the ray sweep
+    // fork: side streams see everything the caller enqueued before this call
+    SideStreams& ss = side_streams();
+    const bool forked = ss.ok && !g_prof.on && !getenv("T2N_BWD_SERIAL");
+    cudaStream_t st_scatter = st, st_ray = st;
+    if (forked) {
+        T2N_CUDA(cudaEventRecord(ss.fork, st));
+        T2N_CUDA(cudaStreamWaitEvent(ss.s[0], ss.fork, 0));
+        T2N_CUDA(cudaStreamWaitEvent(ss.s[1], ss.fork, 0));
+        st_scatter = ss.s[0]; st_ray = ss.s[1];
+    }
+    bool scatter_forked = false, ray_done = false;
+    // ---- appearance backward (it only needs forward state) and, on its own stream, the ray sweep
     {
         AppBwdArgs b;
         memset(&b, 0, sizeof(b));
@@ -561,9 +628,20 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
                 sa.fw = b.fw; sa.dprod = d.dprod; sa.ld = 32 * ngp; sa.ngp = ngp; sa.cap_rows = cap_rows;
                 sa.prod_img = d.prod_img;
                 for (int i = 0; i < 3; ++i) { sa.gap[i] = b.gap[i]; sa.gal[i] = b.gal[i]; }
-                g_prof.start(14, st);
-                rc = launch_app_scatter(sa, dev.sm_count, st);
-                g_prof.stop(st);
+                if (forked) {
+                    T2N_CUDA(cudaEventRecord(ss.mid, st));
+                    T2N_CUDA(cudaStreamWaitEvent(st_scatter, ss.mid, 0));
+                    scatter_forked = true;
+                }
+                // the ray sweep is enqueued here, behind the backward-data kernel in launch order: the persistent
+                // tensor-core CTAs take their SMs first and the sweep's small CTAs fill in as those retire
+                rc = enqueue_ray_backward(field, params, fd, batch, out, scratch, g_rgb_map, g_depth_map, g_weight, trans_grad,
+                                          grads, st_ray);
+                if (rc) return rc;
+                ray_done = true;
+                g_prof.start(14, st_scatter);
+                rc = launch_app_scatter(sa, dev.sm_count, st_scatter);
+                g_prof.stop(st_scatter);
                 if (rc) return rc;
             }
 
@@ -590,17 +668,17 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
             for (int k = 0; k < 32 * ngc; ++k) w.col_off[k] = RB.perm[k];
             rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
             if (rc) return rc;
-            // dBasis[own[s]][comp] = sum dfeat[m][s] prod[m][comp]
-            base(d.dfeat_img, 1, d.prod_img, ngp, grads->basis, nullptr);
-            for (int s = 0; s < 32; ++s) w.row_off[s] = RB.own[s] < field->app_dim ? RB.own[s] * NA : -1;
-            for (int c = 0; c < NA; ++c) w.col_off[c] = c;
-            rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
-            if (rc) return rc;
             // dW3[c][n] = sum h2[m][n] dz3[m][c]
             base(d.h2_img, 4, d.dz3_img, 1, grads->w3, nullptr);
             for (int n = 0; n < 128; ++n) w.row_off[n] = n;
             for (int c = 0; c < 3; ++c) w.col_off[c] = c * 128;
             rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st);
+            if (rc) return rc;
+            // dBasis[own[s]][comp] = sum dfeat[m][s] prod[m][comp]   (behind the scatter kernel that writes the products)
+            base(d.dfeat_img, 1, d.prod_img, ngp, grads->basis, nullptr);
+            for (int s = 0; s < 32; ++s) w.row_off[s] = RB.own[s] < field->app_dim ? RB.own[s] * NA : -1;
+            for (int c = 0; c < NA; ++c) w.col_off[c] = c;
+            rc = launch_wgrad(w, dev.max_smem_optin, dev.sm_count, st_scatter);
             g_prof.stop(st);
             if (rc) return rc;
             b.skip_if_le = cap_rows;        // the FFMA kernel below only handles what overflowed the images
@@ -624,28 +702,20 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
             if (rc) return rc;
         }
     }
-    // ---- ray sweep + density scatter
-    {
-        RayBwdArgs a;
-        memset(&a, 0, sizeof(a));
-        a.f = fd;
-        int line_bytes = 0;
-        for (int i = 0; i < 3; ++i) {
-            a.sp[i] = params->sigma_plane[i]; a.sl[i] = params->sigma_line[i]; a.sc[i] = field->n_sigma[i];
-            a.gsp[i] = grads->sigma_plane[i]; a.gsl[i] = grads->sigma_line[i];
-            if (!a.gsp[i] || !a.gsl[i]) return T2N_E_BADARG;
-            line_bytes += field->grid[2 - i] * field->n_sigma[i] * 4;
+    // ---- ray sweep + density scatter (already enqueued behind the tensor-core backward-data kernel if that path ran)
+    if (!ray_done) {
+        rc = enqueue_ray_backward(field, params, fd, batch, out, scratch, g_rgb_map, g_depth_map, g_weight, trans_grad, grads,
+                                  st_ray);
+        if (rc) return rc;
+    }
+    // join: the caller's stream continues only after both side branches
+    if (forked) {
+        if (scatter_forked) {
+            T2N_CUDA(cudaEventRecord(ss.join[0], st_scatter));
+            T2N_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
         }
-        a.rays = batch->rays; a.R = batch->R; a.S = batch->S; a.white_bg = batch->white_bg;
-        a.z_vals = out->z_vals; a.weight = out->weight; a.sigma_feat = scratch->sigma_feat; a.trans = scratch->trans;
-        a.ray_start = scratch->ray_start; a.ray_count = scratch->ray_count; a.ray_flags = scratch->ray_flags;
-        a.app_rgb = scratch->app_rgb; a.g_rgb = g_rgb_map; a.g_depth = g_depth_map; a.g_weight = g_weight;
-        if (trans_grad) { a.gw_coef = trans_grad->coef; a.depth_gt = trans_grad->depth_gt; a.delta = trans_grad->delta; }
-        line_bytes = 0;
-        const int grid = (batch->R + 3) / 4;
-        g_prof.start(6, st);
-        rc = launch_ray_backward(a, max_quads(field->n_sigma), line_bytes, grid, st);
-        g_prof.stop(st);
+        T2N_CUDA(cudaEventRecord(ss.join[1], st_ray));
+        T2N_CUDA(cudaStreamWaitEvent(st, ss.join[1], 0));
     }
     return rc;
 }

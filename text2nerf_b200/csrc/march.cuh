@@ -142,7 +142,16 @@ __global__ void __launch_bounds__(256) march_kernel(const __grid_constant__ Marc
     const int grp = lane >> 2;
     int n_valid_local = 0;
 
-    for (int r = blockIdx.x * warps_per_cta + warp; r < a.R; r += gridDim.x * warps_per_cta) {
+    // Rays are handed out by a ticket counter (counters[4], zeroed by the caller with the other counters): a warp takes
+    // the next ray when it finishes one, so the grid stays busy until the batch is exhausted whatever the rays' lengths
+    // (with a fixed stride a 4096-ray batch left 85 % of the warps idle while the rest marched a second ray).  Tickets
+    // are drawn in order, so the warps of a CTA still march neighbouring rays of a view at the same time.
+    (void)warps_per_cta;
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(a.counters + 4, 1);
+        r = __shfl_sync(T2N_FULL, r, 0);
+        if (r >= a.R) break;
         const RaySetup rs = ray_setup(f, a.rays, r);
         const float jit = train ? __ldg(a.jitter + r) : 0.f;
         const size_t row = (size_t)r * S;
