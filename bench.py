@@ -365,6 +365,101 @@ def run_reference_arm(args, rank):
     print(json.dumps(line))
 
 
+def shard_equivalence(model, flat, dev, rank, world, S):
+    """max over the 19 gradient tensors of |all-reduced sharded gradient - single-rank full-batch gradient| / max |.| on one
+    4096-ray batch of view 0 (identical rays, jitter and targets on every rank; each rank differentiates its slice)."""
+    import torch.distributed as dist
+    from text2nerf_b200 import dist as t2n_dist
+    from text2nerf_b200.tensorBase import _FusedLossFn
+    g = torch.Generator().manual_seed(4242)
+    R = TRAIN_BATCH
+    full = host_rays(0)
+    rays = full[torch.randint(0, full.shape[0], (R,), generator=g)].contiguous().to(dev)
+    jitter = torch.rand(R, generator=g).to(dev)
+    rgb_gt, depth_gt = torch.rand(R, 3, generator=g).to(dev), (2 + 4 * torch.rand(R, generator=g)).to(dev)
+
+    def run(lo, hi):
+        flat.zero_()
+        loss = _FusedLossFn.apply(model, rays[lo:hi].contiguous(), jitter[lo:hi].contiguous(), S, True,
+                                  rgb_gt[lo:hi].contiguous(), depth_gt[lo:hi].contiguous(), 0.005, 1e3, 0.1, 1.0 / R, True,
+                                  *model._flat_params())[0]
+        loss.backward()
+
+    lo, hi = t2n_dist.shard_bounds(R, rank, world)
+    for _ in range(2):          # first pass sizes the tensor-core backward's operand images
+        run(lo, hi)
+    t2n_dist.allreduce_flat_grads_overlapped(model, world)
+    torch.cuda.synchronize()
+    sharded = flat.clone()
+    err = torch.zeros(1, device=dev)
+    if rank == 0:
+        for _ in range(2):
+            run(0, R)
+        torch.cuda.synchronize()
+        n_den = model._flat_grad["n_density"]
+        worst = 0.0
+        for a, b in ((sharded[:n_den], flat[:n_den]), (sharded[n_den:], flat[n_den:])):
+            worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+        worst_t = 0.0
+        for v in model._flat_grad["views"]:
+            off = (v.data_ptr() - flat.data_ptr()) // 4
+            a, b = sharded[off:off + v.numel()], flat[off:off + v.numel()]
+            worst_t = max(worst_t, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+        err[0] = worst_t
+    dist.broadcast(err, 0)
+    return float(err)
+
+
+def strong_scaling_leg(params, dev, rank, world, timed, steps):
+    """Text2NeRF's own training shape (aabb +-8, 300^3, step_ratio 1.0 -> S = 259, ONE 16384-ray batch per step;
+    text2nerf_main.py:437-439, 662-664) with the batch split over the ranks: strong scaling of a fixed batch."""
+    import contextlib
+    import io
+    from text2nerf_b200 import TensorVMSplit
+    from text2nerf_b200 import dist as t2n_dist
+    R = 16384
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TensorVMSplit(torch.tensor([[-8.0, -8, -8], [8, 8, 8]], device=dev), GRID, dev, density_n_comp=[16, 16, 16],
+                          appearance_n_comp=[48, 48, 48], app_dim=27, near_far=[0.5, 8.0], shadingMode="MLP_Fea_noview",
+                          alphaMask_thres=0.001, density_shift=-10, distance_scale=25, pos_pe=6, view_pe=2, fea_pe=6,
+                          featureC=128, step_ratio=1.0, fea2denseAct="softplus")
+    m.load_state_dict({k: v.to(dev) for k, v in params.items()})
+    S = m.nSamples // 2
+    flat = m.enable_flat_grads(True)
+    if world > 1:
+        t2n_dist.enable_overlapped_allreduce(m)
+    g = torch.Generator().manual_seed(77)
+    pose = torch.tensor([[1.0, 0, 0, 0.1], [0, 1.0, 0, -0.05], [0, 0, 1.0, 0.2]])
+    view = pinhole_rays(512, 512, 512.0, pose)
+    lo, hi = t2n_dist.shard_bounds(R, rank, world)
+    batches = []
+    for _ in range(4):
+        idx = torch.randint(0, view.shape[0], (R,), generator=g)
+        rgb, dep = torch.rand(R, 3, generator=g), 0.5 + 7.5 * torch.rand(R, generator=g)
+        batches.append((view[idx][lo:hi].contiguous().to(dev), rgb[lo:hi].contiguous().to(dev), dep[lo:hi].contiguous().to(dev)))
+    torch.manual_seed(11)
+
+    def step():
+        for rays_b, rgb_gt, depth_gt in batches:
+            flat.zero_()
+            m.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S, n_rays_total=R).backward()
+            t2n_dist.allreduce_flat_grads_overlapped(m, world)
+
+    for _ in range(3):
+        step()
+    ms = timed(step, steps)
+    per_batch = ms / (steps * len(batches))
+    n_app, n_valid = m.app_sample_count()
+    out = {"what": "ONE 16384-ray Text2NeRF training batch (aabb +-8, 300^3, S=259) per step, rays split over the ranks, "
+                   "fused data loss fwd+bwd + the two-segment gradient all-reduce",
+           "total_rays_per_batch": R, "rays_per_rank": hi - lo, "ms_per_batch": per_batch, "value": R / per_batch / 1e3,
+           "unit": "Mrays/s", "scaling": "strong", "listed_per_ray": n_app / max(1, hi - lo), "valid_per_ray": n_valid / max(1, hi - lo)}
+    m.enable_flat_grads(False)
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -485,12 +580,54 @@ def main():
         pass
     achieved = kbytes[dom] / (kavg[dom] * 1e-3) / 1e9
     total_bytes = n_rays * (40 + 8 * S) + n_valid * 1152 + n_app * 3456
+    sm_hz = 1e6 * float((clk.summary().get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0))
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        pass
+
+    def kernel_line(name, ms, alg_bytes, compulsory_bytes, bound, mma_cycles_per_sm=None):
+        """One kernel against the roofs that can bind it.  `algorithmic_*`: SURVEY.md 8d bytes (every gathered texel counted
+        as if it came from HBM) / CUDA-event time -- it may exceed the HBM peak because the 69 MB of factors are L2/L1
+        resident, so it is NOT called a roofline fraction unless HBM is what binds the kernel.  `compulsory_hbm_frac`:
+        bytes that must cross HBM (ray inputs, [R,S] outputs, every touched factor once) / time / peak.
+        `tensor_pipe_frac`: cycles the issued tcgen05.mma instructions occupy the tensor pipe (3xTF32: 3 MMAs per K step of
+        8; 64 cycles at N = 128, 48 at N = 32, tools/mma_rate.cu) / elapsed SM cycles.  ncu_*: the committed
+        `ncu --set full` capture of this workload (profiles/ncu_traffic.json)."""
+        d = {"ms": ms, "bound": bound, "algorithmic_GBps": alg_bytes / (ms * 1e-3) / 1e9,
+             "algorithmic_over_hbm_peak": alg_bytes / (ms * 1e-3) / 1e9 / peak,
+             "compulsory_hbm_frac": compulsory_bytes / (ms * 1e-3) / 1e9 / peak}
+        if mma_cycles_per_sm is not None:
+            d["tensor_pipe_frac"] = mma_cycles_per_sm / (ms * 1e-3 * sm_hz)
+        for k, v in ncu.get(name, {}).items():
+            if k != "source":
+                d["ncu_" + k] = v
+        return d
+
+    factor_bytes = 4 * sum(v.numel() for k, v in params.items() if "plane" in k or "line" in k)
+    tiles_per_sm = n_app / 128.0 / sms
+    # per 128-sample tile: basis 5 chunks at N = 32, layer 1 13 chunks + layer 2 4 chunks at N = 128; 12 MMAs per chunk
+    mma_fwd = tiles_per_sm * 12 * (5 * 48 + 17 * 64)
+    kernels = {
+        "march": kernel_line("march", kavg["march"], kbytes["march"], n_rays * (24 + 8 * S) + factor_bytes * 0.25,
+                             "L1 data-pipe wavefronts of the bilinear gathers + issue (factors are L2/L1 resident; HBM only "
+                             "carries the [R,S] outputs)"),
+        "appearance": kernel_line("appearance", kavg["appearance"], kbytes["appearance"], n_app * 20 + factor_bytes * 0.75,
+                                  "producer warps (gather + decoder columns: issue / chunk hand-off latency); tensor pipe and "
+                                  "HBM both have headroom", mma_fwd),
+        "finalize": kernel_line("finalize", kavg["finalize"], kbytes["finalize"], kbytes["finalize"], "hbm"),
+    }
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "note": "frac = algorithmic gather bytes of the dominant kernel (SURVEY.md 8d: 3476 B per listed sample) / its "
+                        "CUDA-event time / measured HBM copy peak, as the contract defines it; what actually binds each kernel is "
+                        "in `kernels[*].bound` with the matching utilisation",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "kernel_ms": kavg, "kernel_algorithmic_bytes": kbytes,
+                "kernel_ms": kavg, "kernel_algorithmic_bytes": kbytes, "kernels": kernels,
                 "path_algorithmic_GBps": total_bytes / (ms_fwd / args.steps * 1e-3) / 1e9,
-                "path_frac": total_bytes / (ms_fwd / args.steps * 1e-3) / 1e9 / peak,
+                "path_algorithmic_over_hbm_peak": total_bytes / (ms_fwd / args.steps * 1e-3) / 1e9 / peak,
                 "valid_samples_per_ray": n_valid / n_rays, "app_samples_per_ray": n_app / n_rays}
 
     # ---------------- forward + backward on training batches
@@ -505,12 +642,15 @@ def main():
             batches.append((rays_dev[idx.to(dev)].contiguous(), torch.rand(TRAIN_BATCH, 3, generator=g).to(dev),
                             (2 + 4 * torch.rand(TRAIN_BATCH, generator=g)).to(dev)))
         torch.manual_seed(7 + rank)
+        if world > 1:
+            t2n_dist.enable_overlapped_allreduce(model)
+        n_total = world * TRAIN_BATCH       # the means of the loss run over the rays of ALL ranks: no 1/world pass afterwards
 
         def train_step():           # fused data loss (TensorBase.data_loss): forward, loss kernel, backward kernels
             for rays_b, rgb_gt, depth_gt in batches:
                 flat.zero_()
-                model.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S).backward()
-                t2n_dist.allreduce_flat_grads(model, world)
+                model.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S, n_rays_total=n_total).backward()
+                t2n_dist.allreduce_flat_grads_overlapped(model, world)
 
         def train_step_composed():  # the same step written as the reference writes it: tensor ops on the four outputs
             for rays_b, rgb_gt, depth_gt in batches:
@@ -531,7 +671,10 @@ def main():
                    "loss": "rgb MSE + 0.005 depth MSE + 1e3 transmittance (text2nerf_main.py:563-575) through the fused "
                            "TensorBase.data_loss, no optimiser step",
                    "composed_autograd_value": rays_done / (ms_tr_c * 1e-3) / 1e6,
-                   "collective": "1 NCCL all-reduce of the flat fp32 grad buffer per batch" if world > 1 else "none (1 GPU)"}
+                   "collective": ("all-reduce(sum) of the flat fp32 gradient buffer per batch in two segments: appearance factors + "
+                                  "decoder (75 %) on a communication stream as soon as T2NGrads::app_done_event fires, overlapping "
+                                  "the density sweep; density factors after the backward joined; 1/world folded into the loss")
+                   if world > 1 else "none (1 GPU)"}
         lib.t2n_profile_enable(1)
         rays_b, rgb_gt, depth_gt = batches[0]
         flat.zero_()
@@ -541,6 +684,25 @@ def main():
         bk = dict(nat.profile_read())
         lib.t2n_profile_enable(0)
         fwd_bwd["kernel_ms"] = {**fk, **bk}
+        fwd_bwd["kernel_ms_note"] = ("profiled batch runs the backward on ONE stream (clean per-kernel event times); the timed "
+                                     "region forks the ray sweep and the scatter/dBasis branch onto side streams")
+        # roofline of the training batch: algorithmic bytes of SURVEY.md 8d (forward + the same gather bytes again for the
+        # scatter-add + the [R,S] state the backward reads) / time of the whole fwd+bwd / HBM peak
+        b_app, b_valid = model.app_sample_count()
+        tb = TRAIN_BATCH * 16 * S + b_valid * 2 * 1152 + b_app * 2 * 3476
+        ms_b = ms_tr / (args.steps * TRAIN_BATCHES_PER_STEP)
+        km = fwd_bwd["kernel_ms"]
+        fwd_bwd["roofline"] = {
+            "bound": "hbm (denominator); the batch is bound by the L2 atomic / scatter rate and producer latency, see kernels",
+            "algorithmic_bytes_per_batch": tb, "achieved": tb / (ms_b * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": tb / (ms_b * 1e-3) / 1e9 / peak, "valid_samples": b_valid, "listed_samples": b_app,
+            "kernels": {k: {"ms": v, "algorithmic_over_hbm_peak": bts / (v * 1e-3) / 1e9 / peak} for k, v, bts in (
+                ("march", km.get("march", 0.0), TRAIN_BATCH * (24 + 16 * S) + b_valid * 1152),
+                ("appearance", km.get("appearance", 0.0), b_app * 3476),
+                ("app_backward_mma", km.get("app_backward_mma", 0.0), b_app * 2.8e3),
+                ("app_scatter", km.get("app_scatter", 0.0), b_app * 2 * 3476),
+                ("wgrad", km.get("wgrad", 0.0), b_app * 6.4e3),
+                ("ray_backward", km.get("ray_backward", 0.0), TRAIN_BATCH * 16 * S + b_valid * 2 * 1152)) if v > 0}}
         # ---- the whole training iteration of text2nerf_main.py:547-598: data loss + TV regularisers + Adam
         # (TV_weight_density 0.1, TV_weight_app 0.01, configs/text2nerf_scenes.txt:31-32), fused against composed
         from text2nerf_b200.optim import FusedAdam
@@ -555,13 +717,18 @@ def main():
                 for rays_b, rgb_gt, depth_gt in batches:
                     flat.zero_()
                     if fused:
-                        total = model.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S)
+                        # the parameter-only TV terms are identical on every rank: scaled by 1/world they survive the
+                        # summing all-reduce unchanged
+                        total = model.data_loss(rays_b, rgb_gt, depth_gt, white_bg=True, N_samples=S, n_rays_total=n_total)
+                        total = total + (model.TV_loss_density(reg) * 0.1 + model.TV_loss_app(reg) * 0.01) / world
+                        total.backward()
+                        t2n_dist.allreduce_flat_grads_overlapped(model, world)
                     else:
                         total = composed_loss(*model(rays_b, is_train=True, white_bg=True, ndc_ray=0, N_samples=S),
                                               rgb_gt, depth_gt)
-                    total = total + model.TV_loss_density(reg) * 0.1 + model.TV_loss_app(reg) * 0.01
-                    total.backward()
-                    t2n_dist.allreduce_flat_grads(model, world)
+                        total = total + model.TV_loss_density(reg) * 0.1 + model.TV_loss_app(reg) * 0.01
+                        total.backward()
+                        t2n_dist.allreduce_flat_grads(model, world)
                     t2n_dist.attach_flat_grads(model)
                     opt.step()
             return iteration
@@ -580,7 +747,14 @@ def main():
                         "TV_loss_app*0.01, Adam step; fused = data_loss + t2n_tv_* + FusedAdam, composed = tensor-op loss and "
                         "TV on the same render kernels + torch.optim.Adam")
         fwd_bwd["full_iteration"] = full
-        launches_train = 16 * TRAIN_BATCHES_PER_STEP * args.steps    # march, pack, app, finalize, data_loss | pack_bwd, bwd-data, 4 wgrad, (pack_w1, ffma fallback, unpack: early exit), ray_backward
+        launches_train = 17 * TRAIN_BATCHES_PER_STEP * args.steps    # march, pack, app, finalize, data_loss | pack_bwd, bwd-data, app_scatter, 4 wgrad, (pack_w1, ffma fallback, unpack: early exit), ray_backward
+        # ---- N > 1: the sharded step must equal the single-GPU step on the full batch
+        if world > 1:
+            fwd_bwd["shard_equivalence_err"] = shard_equivalence(model, flat, dev, rank, world, S)
+        # ---- strong scaling: ONE 16384-ray Text2NeRF training batch (text2nerf_main.py:662-664) split over the ranks
+        fwd_bwd["strong"] = strong_scaling_leg(params, dev, rank, world, timed, args.steps)
+        if world > 1:
+            t2n_dist.enable_overlapped_allreduce(model, False)
         model.enable_flat_grads(False)
 
     # ---------------- CPU baseline (rank 0, N=1 only) + parity of the product arm on the baseline's own ray samples

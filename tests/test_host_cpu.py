@@ -31,7 +31,7 @@ def test_struct_sizes_match_header_layout():
     # natural alignment, no packing surprises: sizes are what the C compiler produces for the header
     assert C.sizeof(nat.T2NField) == 4 * (9 + 3 + 1 + 2 + 4 + 4 + 6 + 2 + 2)
     assert C.sizeof(nat.T2NParams) == 8 * (12 + 1 + 6 + 2)
-    assert C.sizeof(nat.T2NGrads) == 8 * (12 + 1 + 6)
+    assert C.sizeof(nat.T2NGrads) == 8 * (12 + 1 + 6 + 1)       # + app_done_event
     assert C.sizeof(nat.T2NBatch) == 8 * 2 + 4 * 4
     assert C.sizeof(nat.T2NScratch) == 8 * 19
     assert C.sizeof(nat.T2NAlphaMask) == 8 + 4 * 3 + 4 * 6 + 4   # padded to 8

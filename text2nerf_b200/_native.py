@@ -55,6 +55,7 @@ class T2NGrads(C.Structure):
         ("basis", C.c_void_p),
         ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
         ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("app_done_event", C.c_void_p),
     ]
 
 

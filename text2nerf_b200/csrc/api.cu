@@ -708,12 +708,14 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
                                   st_ray);
         if (rc) return rc;
     }
-    // join: the caller's stream continues only after both side branches
+    // join: the caller's stream continues only after both side branches.  The appearance branch joins first, so the
+    // caller's "appearance gradients complete" event can fire while the ray sweep is still running.
+    if (forked && scatter_forked) {
+        T2N_CUDA(cudaEventRecord(ss.join[0], st_scatter));
+        T2N_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
+    }
+    if (grads->app_done_event) T2N_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(grads->app_done_event), st));
     if (forked) {
-        if (scatter_forked) {
-            T2N_CUDA(cudaEventRecord(ss.join[0], st_scatter));
-            T2N_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
-        }
         T2N_CUDA(cudaEventRecord(ss.join[1], st_ray));
         T2N_CUDA(cudaStreamWaitEvent(st, ss.join[1], 0));
     }

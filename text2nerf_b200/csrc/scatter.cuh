@@ -77,8 +77,14 @@ __global__ void __launch_bounds__(128, 4) app_scatter_kernel(const __grid_consta
             int o00 = 0, o01 = 0, o10 = 0, o11 = 0, lo0 = 0, lo1 = 0;
             float4 t00 = zero4, t01 = zero4, t10 = zero4, t11 = zero4, l0 = zero4, l1 = zero4;
             float4 g00 = zero4, g01 = zero4, g10 = zero4, g11 = zero4, gl0 = zero4, gl1 = zero4;
+            // d loss / d product of this lane's channels, fetched one entry ahead (it comes from HBM and nothing else in
+            // the iteration depends on it until the accumulation at the end)
+            const float* dp_ptr = args.dprod + (size_t)(blk * 32 + 16 * hf) * args.ld + comp;
+            float4 dp_next = (chan_ok && (mine & 1u)) ? ldg4(dp_ptr) : zero4;
             for (int j = 0; j < 16; ++j) {
                 const int src = 16 * hf + j;
+                const float4 dp = dp_next;
+                if (chan_ok && j + 1 < 16 && ((mine >> (j + 1)) & 1u)) dp_next = ldg4(dp_ptr + (size_t)(j + 1) * args.ld);
                 const int ix = __shfl_sync(T2N_FULL, g.i0[0], src), iy = __shfl_sync(T2N_FULL, g.i0[1], src);
                 const int iz = __shfl_sync(T2N_FULL, g.i0[2], src);
                 const float fx = __shfl_sync(T2N_FULL, g.fr[0], src), fy = __shfl_sync(T2N_FULL, g.fr[1], src);
@@ -119,7 +125,6 @@ __global__ void __launch_bounds__(128, 4) app_scatter_kernel(const __grid_consta
                     const float4 pv = f4_fma(se, t11, f4_fma(sw, t10, f4_fma(ne, t01, f4_scale(nw, t00))));
                     const float4 lv = f4_fma(zw1, l1, f4_scale(zw0, l0));
                     prod = f4_mul(pv, lv);
-                    const float4 dp = ldg4(args.dprod + (size_t)(blk * 32 + src) * args.ld + comp);
                     const float4 dpl = f4_mul(dp, lv);
                     const float4 dln = f4_mul(dp, pv);
                     g00 = f4_fma(nw, dpl, g00); g01 = f4_fma(ne, dpl, g01);

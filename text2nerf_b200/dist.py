@@ -48,6 +48,44 @@ def allreduce_flat_grads(model, world: int, group=None) -> torch.Tensor:
     return flat
 
 
+def enable_overlapped_allreduce(model, on: bool = True) -> None:
+    """Prepare the two-segment all-reduce: the backward records an event when the appearance-side gradients are complete
+    (T2NGrads::app_done_event) -- the density sweep still runs on the library's side stream -- and the all-reduce of that
+    segment (75 % of the buffer at 16/48 components) goes out on a communication stream behind the event, overlapping the
+    sweep.  The density segment follows when the backward has joined."""
+    if not on:
+        model._app_done_event = None
+        model._comm_stream = None
+        return
+    dev = model._flat_grad["buffer"].device
+    with torch.cuda.device(dev):
+        model._app_done_event = torch.cuda.Event()
+        model._comm_stream = torch.cuda.Stream(device=dev)
+    # make sure the event handle exists before the first backward hands it to the library
+    model._app_done_event.record(torch.cuda.current_stream(dev))
+
+
+def allreduce_flat_grads_overlapped(model, world: int, group=None) -> torch.Tensor:
+    """All-reduce(sum) of the flat gradient buffer in two segments, the appearance segment overlapped with the density
+    sweep (enable_overlapped_allreduce).  No scaling pass: the caller folds 1/world into the loss
+    (data_loss(n_rays_total=world * rays_per_rank)), so the summed gradients are already the full-batch mean."""
+    fg = model._flat_grad
+    flat, n_den = fg["buffer"], fg["n_density"]
+    if world <= 1:
+        return flat
+    dev = flat.device
+    cur = torch.cuda.current_stream(dev)
+    comm = model._comm_stream
+    comm.wait_event(model._app_done_event)
+    with torch.cuda.stream(comm):
+        w_app = dist.all_reduce(flat[n_den:], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    w_den = dist.all_reduce(flat[:n_den], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    w_app.wait()
+    w_den.wait()
+    cur.wait_stream(comm)
+    return flat
+
+
 def attach_flat_grads(model) -> None:
     """Make the (all-reduced) flat-buffer views the parameters' .grad; gradients that autograd
     already accumulated there (parameter-only regularisers) are kept and added."""

@@ -331,6 +331,8 @@ class TensorVMSplit(TensorBase):
         g.basis = grads[12].data_ptr()
         if self._is_mlp:
             g.w1, g.b1, g.w2, g.b2, g.w3, g.b3 = [t.data_ptr() for t in grads[13:19]]
+        ev = getattr(self, "_app_done_event", None)     # set by text2nerf_b200.dist for the overlapped all-reduce
+        g.app_done_event = ev.cuda_event if ev is not None else None
         return g
 
     def _grads_for_autograd(self, grads: Sequence[torch.Tensor]):
@@ -361,7 +363,9 @@ class TensorVMSplit(TensorBase):
         views = []
         for t, off, n in zip(p_cl, offs, sizes):
             views.append(torch.as_strided(buf, t.shape, t.stride(), off))
-        self._flat_grad = {"buffer": buf, "views": views}
+        # the density factors come first (C-ABI parameter order): [0, n_density) is the segment the ray sweep writes,
+        # the rest (appearance factors, basis, decoder) is complete earlier (T2NGrads::app_done_event)
+        self._flat_grad = {"buffer": buf, "views": views, "n_density": offs[6]}
         return buf
 
     def _refresh_flat_grads(self):

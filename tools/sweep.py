@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 from text2nerf_b200 import TensorVMSplit, ray_utils
+from text2nerf_b200 import _native as nat
 
 dev = torch.device("cuda:0")
 peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -54,7 +55,18 @@ def measure(model, rays, S, reps):
     n_app, n_valid = model.app_sample_count()
     ms_fb = timeit(fb, max(2, reps // 2))
     bytes_f = R * (40 + 8 * S) + n_valid * 1152 + n_app * 3456
-    return {"rays": R, "S": S, "fwd_ms": ms_f, "fwd_Mrays_s": R / ms_f / 1e3, "fwd_bwd_ms": ms_fb, "fwd_bwd_Mrays_s": R / ms_fb / 1e3,
+    kernel_ms = None
+    if os.environ.get("SWEEP_KERNELS"):
+        lib = nat.load()
+        lib.t2n_profile_enable(1)
+        for p in model.parameters():
+            p.grad = None
+        loss = model.data_loss(rays, rgb_gt, depth_gt, white_bg=True, N_samples=S)
+        kernel_ms = dict(nat.profile_read())
+        loss.backward()
+        kernel_ms.update(dict(nat.profile_read()))
+        lib.t2n_profile_enable(0)
+    return {"kernel_ms": kernel_ms,"rays": R, "S": S, "fwd_ms": ms_f, "fwd_Mrays_s": R / ms_f / 1e3, "fwd_bwd_ms": ms_fb, "fwd_bwd_Mrays_s": R / ms_fb / 1e3,
             "valid_per_ray": n_valid / R, "app_per_ray": n_app / R, "fwd_roofline_frac": bytes_f / (ms_f * 1e-3) / 1e9 / peak}
 
 
@@ -65,7 +77,7 @@ S = model.nSamples
 full = ray_utils.camera_rays(bench.view_pose(0), bench.H, bench.W, [bench.FOCAL] * 2, normalize=True, device=dev)
 g = torch.Generator().manual_seed(0)
 out["sweep_lego_300"] = []
-for e in range(10, 21):
+for e in ([] if os.environ.get("SWEEP_T2N_ONLY") else range(10, 21)):
     R = 1 << e
     idx = torch.randint(0, full.shape[0], (R,), generator=g).to(dev)
     rays = full[idx].contiguous()
