@@ -396,10 +396,6 @@ def shard_equivalence(model, flat, dev, rank, world, S):
         for _ in range(2):
             run(0, R)
         torch.cuda.synchronize()
-        n_den = model._flat_grad["n_density"]
-        worst = 0.0
-        for a, b in ((sharded[:n_den], flat[:n_den]), (sharded[n_den:], flat[n_den:])):
-            worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
         worst_t = 0.0
         for v in model._flat_grad["views"]:
             off = (v.data_ptr() - flat.data_ptr()) // 4
@@ -671,9 +667,10 @@ def main():
                    "loss": "rgb MSE + 0.005 depth MSE + 1e3 transmittance (text2nerf_main.py:563-575) through the fused "
                            "TensorBase.data_loss, no optimiser step",
                    "composed_autograd_value": rays_done / (ms_tr_c * 1e-3) / 1e6,
-                   "collective": ("all-reduce(sum) of the flat fp32 gradient buffer per batch in two segments: appearance factors + "
-                                  "decoder (75 %) on a communication stream as soon as T2NGrads::app_done_event fires, overlapping "
-                                  "the density sweep; density factors after the backward joined; 1/world folded into the loss")
+                   "collective": ("all-reduce(sum) of the flat fp32 gradient buffer per batch in two segments: appearance factors (75 %) "
+                                  "on a communication stream as soon as T2NGrads::app_done_event fires (behind the scatter kernel), "
+                                  "overlapping the weight-gradient GEMMs and the density sweep; density factors + basis + decoder "
+                                  "after the backward joined; 1/world folded into the loss")
                    if world > 1 else "none (1 GPU)"}
         lib.t2n_profile_enable(1)
         rays_b, rgb_gt, depth_gt = batches[0]

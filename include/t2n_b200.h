@@ -107,10 +107,11 @@ typedef struct T2NGrads {
     float* app_line[3];
     float* basis;
     float* w1; float* b1; float* w2; float* b2; float* w3; float* b3;
-    /* Optional cudaEvent_t (NULL = none).  The backward records it on `stream` at the point where every appearance-side
-     * gradient (app planes / lines, basis, decoder) is complete while the density sweep -- which the backward runs on a
-     * side stream -- may still be in flight: a data-parallel caller starts the all-reduce of that segment of its flat
-     * gradient buffer on a communication stream behind this event, so the collective overlaps the sweep. */
+    /* Optional cudaEvent_t (NULL = none).  The backward records it at the point where the gradients of the appearance
+     * FACTORS (app_plane, app_line: 75 % of all gradient bytes at 16/48 components) are complete, while the weight-gradient
+     * GEMMs and the density sweep -- which run on other streams of the backward's fork -- are still in flight: a
+     * data-parallel caller starts the all-reduce of that segment of its flat gradient buffer on a communication stream
+     * behind this event, so the collective overlaps the rest of the backward. */
     void* app_done_event;
 } T2NGrads;
 

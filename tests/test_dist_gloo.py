@@ -48,6 +48,17 @@ def _worker(rank, world, port, q):
         expect = [(pr * 1.0).sum(0).expand_as(v) / world for v, pr in zip(model._flat_grad["views"], per_ray)]
         ok = all(torch.allclose(p.grad if i else p.grad - 0.5, e, atol=1e-5)
                  for i, (p, e) in enumerate(zip(model._flat_params(), expect)))
+        # the two-segment form (appearance factors first, 1/world folded into the loss by the caller): plain sums
+        flat.zero_()
+        for p in model._flat_params():
+            p.grad = None
+        for v, pr in zip(model._flat_grad["views"], per_ray):
+            v.add_((pr[lo:hi] * torch.ones_like(v)[None]).sum(0) / world)
+        n_early = model._flat_grad["n_early"]
+        assert n_early == sum((v.numel() + 3) & ~3 for v in model._flat_grad["views"][6:12])
+        assert model._flat_grad["views"][6].data_ptr() == flat.data_ptr()        # app_plane.0 leads the buffer
+        t2n_dist.allreduce_flat_grads_overlapped(model, world)
+        ok = ok and all(torch.allclose(v, e, atol=1e-5) for v, e in zip(model._flat_grad["views"], expect))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

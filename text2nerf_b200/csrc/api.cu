@@ -540,7 +540,7 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
         T2N_CUDA(cudaStreamWaitEvent(ss.s[1], ss.fork, 0));
         st_scatter = ss.s[0]; st_ray = ss.s[1];
     }
-    bool scatter_forked = false, ray_done = false;
+    bool scatter_forked = false, ray_done = false, app_event_done = false;
     // ---- appearance backward (it only needs forward state) and, on its own stream, the ray sweep
     {
         AppBwdArgs b;
@@ -643,6 +643,11 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
                 rc = launch_app_scatter(sa, dev.sm_count, st_scatter);
                 g_prof.stop(st_scatter);
                 if (rc) return rc;
+                // the appearance planes / lines (75 % of all gradient bytes) are complete here
+                if (grads->app_done_event) {
+                    T2N_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(grads->app_done_event), st_scatter));
+                    app_event_done = true;
+                }
             }
 
             WgradArgs w;
@@ -708,13 +713,13 @@ int t2n_render_backward_tg(const T2NField* field, const T2NParams* params, const
                                   st_ray);
         if (rc) return rc;
     }
-    // join: the caller's stream continues only after both side branches.  The appearance branch joins first, so the
-    // caller's "appearance gradients complete" event can fire while the ray sweep is still running.
+    // join: the caller's stream continues only after both side branches
     if (forked && scatter_forked) {
         T2N_CUDA(cudaEventRecord(ss.join[0], st_scatter));
         T2N_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
     }
-    if (grads->app_done_event) T2N_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(grads->app_done_event), st));
+    if (grads->app_done_event && !app_event_done)      // FFMA path: the factor gradients are complete with the app kernels
+        T2N_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(grads->app_done_event), st));
     if (forked) {
         T2N_CUDA(cudaEventRecord(ss.join[1], st_ray));
         T2N_CUDA(cudaStreamWaitEvent(st, ss.join[1], 0));

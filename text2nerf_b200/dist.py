@@ -49,10 +49,11 @@ def allreduce_flat_grads(model, world: int, group=None) -> torch.Tensor:
 
 
 def enable_overlapped_allreduce(model, on: bool = True) -> None:
-    """Prepare the two-segment all-reduce: the backward records an event when the appearance-side gradients are complete
-    (T2NGrads::app_done_event) -- the density sweep still runs on the library's side stream -- and the all-reduce of that
-    segment (75 % of the buffer at 16/48 components) goes out on a communication stream behind the event, overlapping the
-    sweep.  The density segment follows when the backward has joined."""
+    """Prepare the two-segment all-reduce: the backward records an event when the gradients of the appearance factors are
+    complete (T2NGrads::app_done_event, right behind the scatter kernel) -- the weight-gradient GEMMs and the density sweep
+    still run on the other streams of the backward's fork -- and the all-reduce of that segment (the front 75 % of the flat
+    buffer at 16/48 components) goes out on a communication stream behind the event, overlapping the rest of the
+    backward.  The remainder (density factors, basis, decoder) follows when the backward has joined."""
     if not on:
         model._app_done_event = None
         model._comm_stream = None
@@ -70,16 +71,20 @@ def allreduce_flat_grads_overlapped(model, world: int, group=None) -> torch.Tens
     sweep (enable_overlapped_allreduce).  No scaling pass: the caller folds 1/world into the loss
     (data_loss(n_rays_total=world * rays_per_rank)), so the summed gradients are already the full-batch mean."""
     fg = model._flat_grad
-    flat, n_den = fg["buffer"], fg["n_density"]
+    flat, n_early = fg["buffer"], fg["n_early"]
     if world <= 1:
+        return flat
+    if not flat.is_cuda:                    # host tensors (gloo tests of the segment logic): no streams to overlap on
+        dist.all_reduce(flat[:n_early], op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(flat[n_early:], op=dist.ReduceOp.SUM, group=group)
         return flat
     dev = flat.device
     cur = torch.cuda.current_stream(dev)
     comm = model._comm_stream
     comm.wait_event(model._app_done_event)
     with torch.cuda.stream(comm):
-        w_app = dist.all_reduce(flat[n_den:], op=dist.ReduceOp.SUM, group=group, async_op=True)
-    w_den = dist.all_reduce(flat[:n_den], op=dist.ReduceOp.SUM, group=group, async_op=True)
+        w_app = dist.all_reduce(flat[:n_early], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    w_den = dist.all_reduce(flat[n_early:], op=dist.ReduceOp.SUM, group=group, async_op=True)
     w_app.wait()
     w_den.wait()
     cur.wait_stream(comm)

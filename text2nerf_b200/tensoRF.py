@@ -354,18 +354,22 @@ class TensorVMSplit(TensorBase):
         params = self._flat_params()
         p_cl = self._native_param_tensors(params)
         sizes = [t.numel() for t in p_cl]
-        # keep every segment 16-byte aligned for the vector atomics
-        offs, o = [], 0
-        for n in sizes:
-            offs.append(o)
-            o += (n + 3) & ~3
+        # Buffer order: the appearance factors (C-ABI parameters 6..11) come FIRST -- they are complete earliest in the
+        # backward (T2NGrads::app_done_event) and form the segment whose all-reduce overlaps the rest -- then the density
+        # factors, basis and decoder.  Every segment stays 16-byte aligned for the vector atomics.
+        order = list(range(6, 12)) + list(range(0, 6)) + list(range(12, len(p_cl)))
+        offs, o = [0] * len(p_cl), 0
+        n_early = 0
+        for j in order:
+            offs[j] = o
+            o += (sizes[j] + 3) & ~3
+            if j == 11:
+                n_early = o
         buf = torch.zeros((o,), device=p_cl[0].device, dtype=torch.float32)
         views = []
-        for t, off, n in zip(p_cl, offs, sizes):
+        for t, off in zip(p_cl, offs):
             views.append(torch.as_strided(buf, t.shape, t.stride(), off))
-        # the density factors come first (C-ABI parameter order): [0, n_density) is the segment the ray sweep writes,
-        # the rest (appearance factors, basis, decoder) is complete earlier (T2NGrads::app_done_event)
-        self._flat_grad = {"buffer": buf, "views": views, "n_density": offs[6]}
+        self._flat_grad = {"buffer": buf, "views": views, "n_early": n_early}
         return buf
 
     def _refresh_flat_grads(self):
