@@ -329,6 +329,35 @@ int t2n_resample_plane(const float* src, int H, int W, int C, float* dst, int H2
 int t2n_crop_plane(const float* src, int H, int W, int C, int y0, int x0, float* dst, int H2, int W2,
                    t2n_stream_t stream);
 
+/* ---- render-side consumers of a rendered RGB-D view ------------------------------------- */
+
+/* Warper.forward_warp (scripts/Warper.py:21-62, 64-172): DIBR re-projection of a view into a second camera by bilinear
+ * splatting with depth-ordered weights, in float64 like the reference's numpy arithmetic.  frame [h][w][3] uint8,
+ * mask [h][w] 0/1 (NULL = all known), depth [h][w] double: device.  M = transformation2 @ inv(transformation1) (16),
+ * K1inv = inv(intrinsic1) (9), K2 = intrinsic2 (9): HOST doubles, row-major.  scratch: device doubles, at least
+ * t2n_forward_warp_scratch_doubles(h, w).  Outputs (device): out_frame [h][w][3] uint8, out_mask [h][w] 0/1,
+ * out_depth [h][w] double, flow [h][w][2] double (= Warper's warped_frame2, mask2, warped_depth2, flow12). */
+size_t t2n_forward_warp_scratch_doubles(int h, int w);
+int t2n_forward_warp(const unsigned char* frame, const unsigned char* mask, const double* depth, const double* M_host,
+                     const double* K1inv_host, const double* K2_host, int h, int w, double* scratch,
+                     unsigned char* out_frame, unsigned char* out_mask, double* out_depth, double* flow, t2n_stream_t stream);
+
+/* One iteration of sparse_bilateral_filtering (dataLoader/bilateral_filtering.py:5-35) on fp32 images [H][W]:
+ * t2n_depth_discontinuity = vis_depth_discontinuity + the discontinuity map (:17-24, 72-95): disc = clip(u+b+l+r over
+ * threshold of the disparity differences, 0, 1), 1 where depth0 == 0, 0 where mask == 0 (mask NULL = none).
+ * t2n_weighted_median = bilateral_filter with that map (:138-186): the weighted median over the window of every pixel
+ * whose window touches a discontinuity (window odd, <= 9); other pixels copy the rim-replaced input. */
+int t2n_depth_discontinuity(const float* vis_depth, const float* depth0, const unsigned char* mask, float threshold,
+                            int H, int W, float* disc, t2n_stream_t stream);
+int t2n_weighted_median(const float* in, const float* disc, const unsigned char* mask, int H, int W, int window,
+                        float* out, t2n_stream_t stream);
+
+/* Per-view assembly of renderer.evaluation (renderer.py:92-96, 98-101, 112): rgb8 = uint8(clamp(rgb, 0, 1) * 255),
+ * depth_out = max(depth + depth_shift, 0), and (gt != NULL) sq_err[0] = sum (clamp(rgb) - gt)^2 in float64 (the caller
+ * turns it into the PSNR).  rgb [n][3], depth [n], gt [n][3] fp32. */
+int t2n_assemble_view(const float* rgb, const float* depth, const float* gt, long long n, float depth_shift,
+                      unsigned char* rgb8, float* depth_out, double* sq_err, t2n_stream_t stream);
+
 /* Measurement aid (bench.py roofline leg; not part of the reference surface).  While enabled,
  * every forward/backward call records CUDA events on its stream around each kernel it launches.
  * t2n_profile_read synchronises on the last event and writes up to n (kernel id, milliseconds)

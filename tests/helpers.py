@@ -16,7 +16,7 @@ REFERENCE_DIR = "/root/reference"
 
 def golden_names(kind=None):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    names = [n for n in names if n not in ("get_rays", "f3_maintenance", "sh_eval")]
+    names = [n for n in names if n not in ("get_rays", "f3_maintenance", "sh_eval", "f4_consumers")]
     if kind == "train":
         names = [n for n in names if "train" in n]
     return names

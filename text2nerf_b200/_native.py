@@ -140,6 +140,14 @@ SYMBOLS = {
     "t2n_resample_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "t2n_crop_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p]),
+    "t2n_forward_warp_scratch_doubles": (C.c_size_t, [C.c_int, C.c_int]),
+    "t2n_forward_warp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "t2n_depth_discontinuity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "t2n_weighted_median": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "t2n_assemble_view": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
     "t2n_compute_alpha": (C.c_int, [C.POINTER(T2NField), C.POINTER(T2NParams), C.POINTER(T2NAlphaMask),
                                     C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
 }

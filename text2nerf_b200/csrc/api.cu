@@ -7,6 +7,7 @@
 #include "launch.h"
 #include "rays.cuh"
 #include "maintenance.cuh"
+#include "consumers.cuh"
 
 using namespace t2n;
 
@@ -843,6 +844,57 @@ int t2n_crop_plane(const float* src, int H, int W, int C, int y0, int x0, float*
     if (y0 < 0 || x0 < 0 || y0 + H2 > H || x0 + W2 > W) return T2N_E_BADARG;
     a.y0 = y0; a.x0 = x0;
     return launch_crop_plane(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t t2n_forward_warp_scratch_doubles(int h, int w) {
+    if (h <= 0 || w <= 0) return 0;
+    return (size_t)(h + 2) * (w + 2) * 5 + (size_t)h * w + 2;
+}
+
+int t2n_forward_warp(const unsigned char* frame, const unsigned char* mask, const double* depth, const double* M_host,
+                     const double* K1inv_host, const double* K2_host, int h, int w, double* scratch,
+                     unsigned char* out_frame, unsigned char* out_mask, double* out_depth, double* flow, t2n_stream_t stream) {
+    if (!frame || !depth || !M_host || !K1inv_host || !K2_host || !scratch || !out_frame || !out_mask || !out_depth || !flow ||
+        h <= 0 || w <= 0)
+        return T2N_E_BADARG;
+    WarpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.frame = frame; a.mask = mask; a.depth = depth; a.h = h; a.w = w;
+    memcpy(a.M, M_host, sizeof(a.M)); memcpy(a.K1inv, K1inv_host, sizeof(a.K1inv)); memcpy(a.K2, K2_host, sizeof(a.K2));
+    const size_t canvas = (size_t)(h + 2) * (w + 2);
+    a.acc_img = scratch; a.acc_depth = scratch + 3 * canvas; a.acc_w = scratch + 4 * canvas;
+    a.trans_depth = scratch + 5 * canvas;
+    a.max_log = reinterpret_cast<unsigned long long*>(scratch + 5 * canvas + (size_t)h * w);
+    a.flow = flow; a.out_frame = out_frame; a.out_mask = out_mask; a.out_depth = out_depth;
+    return launch_forward_warp(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2n_depth_discontinuity(const float* vis_depth, const float* depth0, const unsigned char* mask, float threshold,
+                            int H, int W, float* disc, t2n_stream_t stream) {
+    if (!vis_depth || !depth0 || !disc || H < 3 || W < 3) return T2N_E_BADARG;
+    DiscArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vis_depth = vis_depth; a.depth0 = depth0; a.mask = mask; a.threshold = threshold; a.H = H; a.W = W; a.disc = disc;
+    return launch_discontinuity(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2n_weighted_median(const float* in, const float* disc, const unsigned char* mask, int H, int W, int window,
+                        float* out, t2n_stream_t stream) {
+    if (!in || !disc || !out || H < 3 || W < 3 || window < 1 || window > 9 || !(window & 1)) return T2N_E_BADARG;
+    MedianArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in; a.disc = disc; a.mask = mask; a.H = H; a.W = W; a.window = window; a.out = out;
+    return launch_weighted_median(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2n_assemble_view(const float* rgb, const float* depth, const float* gt, long long n, float depth_shift,
+                      unsigned char* rgb8, float* depth_out, double* sq_err, t2n_stream_t stream) {
+    if (!rgb || !depth || !rgb8 || !depth_out || n <= 0 || (gt && !sq_err)) return T2N_E_BADARG;
+    AssembleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rgb = rgb; a.depth = depth; a.gt = gt; a.n = n; a.depth_shift = depth_shift; a.rgb8 = rgb8; a.depth_out = depth_out;
+    a.sq_err = gt ? sq_err : nullptr;
+    return launch_assemble(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

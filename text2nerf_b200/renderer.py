@@ -44,3 +44,28 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
     # view at S = 1036) for nothing
     rgbs, depth_maps, z_val, weights = (p[0] if len(p) == 1 else torch.cat(p) for p in parts)
     return rgbs, None, depth_maps, weights, z_val
+
+
+@torch.no_grad()
+def evaluation_views(all_rays, tensorf, img_wh, all_rgbs=None, N_vis=5, N_samples=-1, white_bg=True, ndc_ray=False,
+                     push_depth=2.0, device='cuda', chunk=4096):
+    """The render loop of renderer.evaluation (renderer.py:81-101, 112-113) without its file / video / LPIPS side: every
+    N-th view of `all_rays` [n_views, H*W, 6] is rendered and assembled ON THE DEVICE (clamp, uint8 image, shifted depth,
+    PSNR against all_rgbs when given); only the finished uint8 image and the depth map cross to the host, once per view.
+    Returns (PSNRs, rgb_maps [list of (H, W, 3) uint8 numpy], depth_maps [list of (H, W) float32 numpy])."""
+    from .consumers import assemble_view
+    W, H = img_wh
+    step = 1 if N_vis < 0 else max(all_rays.shape[0] // N_vis, 1)
+    idxs = list(range(0, all_rays.shape[0], step))
+    PSNRs, rgb_maps, depth_maps = [], [], []
+    for idx in idxs:
+        rays = all_rays[idx].view(-1, all_rays.shape[-1])
+        rgb_map, _, depth_map, _, _ = OctreeRender_trilinear_fast(rays, tensorf, chunk=chunk, N_samples=N_samples, ndc_ray=ndc_ray,
+                                                                 white_bg=white_bg, device=device)
+        gt = None if all_rgbs is None else all_rgbs[idx].view(H, W, 3)
+        rgb8, depth, psnr = assemble_view(rgb_map, depth_map, H, W, push_depth=push_depth, gt_rgb=gt)
+        if psnr is not None:
+            PSNRs.append(psnr)
+        rgb_maps.append(rgb8.cpu().numpy())
+        depth_maps.append(depth.cpu().numpy())
+    return PSNRs, rgb_maps, depth_maps
