@@ -26,6 +26,7 @@ struct AdamTable {
     float bc1, bc2_sqrt;                    // 1 - beta1^t, sqrt(1 - beta2^t)
 };
 
+#ifdef T2N_KERNELS_TRAINING     // instantiated by exactly one translation unit
 static __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable a) {
     int t = 0;
     while (t + 1 < a.n_tensors && (int)blockIdx.x >= a.chunk_begin[t + 1]) ++t;
@@ -57,5 +58,6 @@ static __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant_
         }
     }
 }
+#endif
 
 }  // namespace t2n

@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(256, 1) app_forward_kernel(const __grid_consta
 }
 
 // Column-permuted, zero-padded copy of W1: w1p[n][k] = perm[k] >= 0 ? w1[n][perm[k]] : 0
+#ifdef T2N_KERNELS_PACK_W1     // instantiated by exactly one translation unit
 static __global__ void pack_w1_kernel(const float* __restrict__ w1, const int32_t* __restrict__ perm, int C, int K, int Kp,
                                float* __restrict__ w1p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,5 +391,6 @@ static __global__ void pack_w1_kernel(const float* __restrict__ w1, const int32_
     const int src = perm[k];
     w1p[i] = src >= 0 ? w1[(size_t)n * K + src] : 0.f;
 }
+#endif
 
 }  // namespace t2n

@@ -872,6 +872,7 @@ __global__ void __launch_bounds__(256, 1) app_backward_kernel(const __grid_const
 }
 
 // g_w1[n][perm[k]] += g_w1p[n][k]
+#ifdef T2N_KERNELS_UNPACK_W1     // instantiated by exactly one translation unit
 static __global__ void unpack_w1_grad_kernel(const float* __restrict__ gw1p, const int32_t* __restrict__ perm, int C, int K,
                                       int Kp, float* __restrict__ gw1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -880,5 +881,6 @@ static __global__ void unpack_w1_grad_kernel(const float* __restrict__ gw1p, con
     const int dst = perm[k];
     if (dst >= 0) gw1[(size_t)n * K + dst] += gw1p[i];
 }
+#endif
 
 }  // namespace t2n

@@ -1,4 +1,5 @@
 // appearance backward launchers
+#define T2N_KERNELS_UNPACK_W1
 #include "launch.h"
 namespace t2n {
 template <int NQ, int NJ>

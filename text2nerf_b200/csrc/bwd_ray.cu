@@ -1,4 +1,5 @@
 // ray sweep backward + fused data loss launchers
+#define T2N_KERNELS_TRAINING
 #include "launch.h"
 namespace t2n {
 // one warp per ray, four rays per CTA, no state shared inside a CTA: the block scheduler balances rays of different

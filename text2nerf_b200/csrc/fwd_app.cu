@@ -1,4 +1,5 @@
 // K2 launchers
+#define T2N_KERNELS_PACK_W1
 #include "launch.h"
 namespace t2n {
 template <int NQ, int NJ>

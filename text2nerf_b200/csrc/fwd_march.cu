@@ -1,4 +1,5 @@
 // K1 + K3 launchers
+#define T2N_KERNELS_FINALIZE
 #include "launch.h"
 namespace t2n {
 template <int NQ>

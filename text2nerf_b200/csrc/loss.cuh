@@ -31,6 +31,7 @@ struct DataLossArgs {
     float* g_weight;            // [R][S] or NULL
 };
 
+#ifdef T2N_KERNELS_TRAINING     // instantiated by exactly one translation unit
 static __global__ void __launch_bounds__(256) data_loss_kernel(const __grid_constant__ DataLossArgs a) {
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -70,5 +71,6 @@ static __global__ void __launch_bounds__(256) data_loss_kernel(const __grid_cons
         a.ray_terms[r * 3 + 2] = mean_w * mean_w;
     }
 }
+#endif
 
 }  // namespace t2n

@@ -280,6 +280,7 @@ struct FinalizeArgs {
     int white_bg;
 };
 
+#ifdef T2N_KERNELS_FINALIZE     // instantiated by exactly one translation unit
 static __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs a) {
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -308,5 +309,6 @@ static __global__ void __launch_bounds__(256) finalize_kernel(const __grid_const
         a.depth_map[r] = __fadd_rn(a.dsum[r], __fmul_rn(__fsub_rn(1.0f, acc), dz));
     }
 }
+#endif
 
 }  // namespace t2n

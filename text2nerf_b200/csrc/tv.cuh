@@ -23,6 +23,7 @@ struct TvArgs {
 
 __device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
+#ifdef T2N_KERNELS_TRAINING     // instantiated by exactly one translation unit
 static __global__ void __launch_bounds__(256) tv_sums_kernel(const __grid_constant__ TvArgs a) {
     const long long n4 = (long long)a.H * a.W * a.C / 4;
     const int rowf = a.W * a.C;     // floats per image row
@@ -47,7 +48,9 @@ static __global__ void __launch_bounds__(256) tv_sums_kernel(const __grid_consta
         a.partials[blockIdx.x * 2 + 1] = tw;
     }
 }
+#endif
 
+#ifdef T2N_KERNELS_TRAINING     // instantiated by exactly one translation unit
 static __global__ void __launch_bounds__(256) tv_grad_kernel(const __grid_constant__ TvArgs a) {
     const long long n4 = (long long)a.H * a.W * a.C / 4;
     const int rowf = a.W * a.C;
@@ -69,5 +72,6 @@ static __global__ void __launch_bounds__(256) tv_grad_kernel(const __grid_consta
         *gp = cur;
     }
 }
+#endif
 
 }  // namespace t2n
