@@ -21,6 +21,7 @@ with contextlib.redirect_stdout(io.StringIO()):
                           app_dim=27, near_far=bench.NEAR_FAR, shadingMode="MLP_Fea_noview", step_ratio=bench.STEP_RATIO,
                           fea_pe=6, view_pe=2)
 model.load_state_dict({k: v.to(dev) for k, v in params.items()})
+S = model.nSamples
 rays = ray_utils.camera_rays(bench.view_pose(0), bench.H, bench.W, [bench.FOCAL] * 2, device=dev)
 g = torch.Generator().manual_seed(0)
 for _ in range(2):
@@ -40,7 +41,7 @@ if os.environ.get("T2N_BWD_FFMA"):
     tot = sum(v[:12])
 else:
     names = ["P1 dz3,dz2 -> TMEM + images", "wait dh1 MMA", "P2 dz1 -> TMEM + image", "P3 dA ring: PE backward + column images",
-             "P4 dfeat", "P5 gather + products image + dprod + scatter"]
+             "P4 dfeat", "P5 dprod -> global (gather + scatter: app_scatter_kernel)"]
     nt = max(v[8], 1)
     print("tensor-core backward-data kernel, tiles (128 samples) of CTA0:", v[8], " total cycles/tile:", sum(v[:6]) / nt)
     tot = sum(v[:6])
