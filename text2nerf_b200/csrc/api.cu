@@ -331,7 +331,12 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
         const bool use_mma = scratch->mma_pack != nullptr && mma_recipe(field, R);
         if (use_mma) {
             g_prof.start(1, st);
-            rc = launch_pack_mma(aa, R, params->w1, field->mlp_in, scratch->mma_pack, st);
+            // The role-specialised kernel (appearance_mma2.cuh) carries the view direction through the basis GEMM, which needs three
+            // padding columns in the last basis chunk; T2N_APP_V1 / the accuracy-study and trace hooks select the first kernel.
+            const bool has_view = field->shading != T2N_SHADE_MLP_FEA_NOVIEW;
+            const bool use_v2 = !getenv("T2N_APP_V1") && !getenv("T2N_MMA_TERMS") && !getenv("T2N_MMA_TRACE") &&
+                                (!has_view || (aa.n_app_total % 32) != 0);
+            rc = launch_pack_mma(aa, R, params->w1, field->mlp_in, scratch->mma_pack, (use_v2 && has_view) ? 1 : 0, st);
             g_prof.stop(st);
             if (rc) return rc;
             AppMmaArgs ma2;
@@ -355,10 +360,11 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
                 const char* denv = getenv("T2N_MMA_DBG");
                 ma2.dbg = denv ? atoi(denv) : 0;
             }
-            const int smem_bytes = mma_smem_layout().total;
+            const int smem_bytes = use_v2 ? app_forward_mma2_smem_bytes() : mma_smem_layout().total;
             if (smem_bytes > dev.max_smem_optin) return T2N_E_SHADING;
             g_prof.start(2, st);
-            rc = launch_app_forward_mma(ma2, smem_bytes, getenv("T2N_FWD_GRID") ? atoi(getenv("T2N_FWD_GRID")) : dev.sm_count, st);
+            const int grid_mma = getenv("T2N_FWD_GRID") ? atoi(getenv("T2N_FWD_GRID")) : dev.sm_count;
+            rc = use_v2 ? launch_app_forward_mma2(ma2, smem_bytes, grid_mma, st) : launch_app_forward_mma(ma2, smem_bytes, grid_mma, st);
             g_prof.stop(st);
             if (rc) return rc;
         } else {

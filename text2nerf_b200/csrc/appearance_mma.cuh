@@ -39,9 +39,11 @@ namespace t2n {
 
 // One thread per (matrix, chunk, row, 16-byte column group): writes hi and lo swizzled images.
 struct PackPerm { short perm[32 * (1 + 2 * kMaxFreq)]; };
+// view_rows != 0: basis rows app_dim..app_dim+2 get a 1 at columns n_app_total..n_app_total+2, so that the basis GEMM copies
+// the view direction the gather puts into those (padding) columns of A into D0 (appearance_mma2.cuh).
 static __global__ void pack_mma_weights_kernel(const float* __restrict__ basis, int app_dim, int n_app_total,
                                                const float* __restrict__ w1, const __grid_constant__ PackPerm perm, int K,
-                                               int Kp, const float* __restrict__ w2, float* __restrict__ out) {
+                                               int Kp, const float* __restrict__ w2, float* __restrict__ out, int view_rows) {
     const MmaPack P = mma_pack_layout(n_app_total, Kp);
     const int total_groups = (P.basis_chunks * 32 + P.w1_chunks * 128 + P.w2_chunks * 128) * 8;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,6 +59,7 @@ static __global__ void pack_mma_weights_kernel(const float* __restrict__ basis, 
         for (int q = 0; q < 4; ++q) {
             const int k = c * 32 + j * 4 + q;
             v[q] = (r < app_dim && k < n_app_total) ? basis[(size_t)r * n_app_total + k] : 0.f;
+            if (view_rows && r >= app_dim && r < app_dim + 3 && k == n_app_total + (r - app_dim)) v[q] = 1.f;
         }
         dst_hi = out + P.basis_off + (size_t)c * 2 * 32 * 32;
     } else if ((rowid -= P.basis_chunks * 32) < P.w1_chunks * 128) {

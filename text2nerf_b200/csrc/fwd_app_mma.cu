@@ -1,6 +1,7 @@
 // tensor-core K2 launchers
 #include "launch.h"
 #include "appearance_mma.cuh"
+#include "appearance_mma2.cuh"
 namespace t2n {
 int launch_app_forward_mma(const AppMmaArgs& a, int smem_bytes, int grid, cudaStream_t st) {
     // the cycle-counter instantiation is only launched by tools/trace_mma.py (T2N_MMA_TRACE)
@@ -10,12 +11,19 @@ int launch_app_forward_mma(const AppMmaArgs& a, int smem_bytes, int grid, cudaSt
     kern<<<grid, kMmaThreads, smem_bytes, st>>>(a);
     return (int)cudaGetLastError();
 }
-int launch_pack_mma(const AppArgs& a, const MmaRecipe& R, const float* w1, int K, float* out, cudaStream_t st) {
+int launch_app_forward_mma2(const AppMmaArgs& a, int smem_bytes, int grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(app_forward_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    app_forward_mma2_kernel<<<grid, kV2Threads, smem_bytes, st>>>(a);
+    return (int)cudaGetLastError();
+}
+int app_forward_mma2_smem_bytes() { return v2_smem_layout().total; }
+int launch_pack_mma(const AppArgs& a, const MmaRecipe& R, const float* w1, int K, float* out, int view_rows, cudaStream_t st) {
     const MmaPack P = mma_pack_layout(a.n_app_total, R.Kp);
     const int groups = (P.basis_chunks * 32 + P.w1_chunks * 128 + P.w2_chunks * 128) * 8;
     PackPerm pp;
     for (int i = 0; i < (int)(sizeof(pp.perm) / sizeof(pp.perm[0])); ++i) pp.perm[i] = R.perm[i];
-    pack_mma_weights_kernel<<<(groups + 255) / 256, 256, 0, st>>>(a.basis, a.app_dim, a.n_app_total, w1, pp, K, R.Kp, a.w2, out);
+    pack_mma_weights_kernel<<<(groups + 255) / 256, 256, 0, st>>>(a.basis, a.app_dim, a.n_app_total, w1, pp, K, R.Kp, a.w2, out, view_rows);
     return (int)cudaGetLastError();
 }
 }  // namespace t2n
