@@ -95,6 +95,20 @@ __device__ __forceinline__ void mbar_wait_hint_a(uint32_t bar_addr, uint32_t par
         "T2N_DONEA_%=:\n\t}"
         :: "r"(bar_addr), "r"(parity), "r"(ns) : "memory");
 }
+// For the roles that run far ahead of the tensor pipe (gather warps, weight loaders): a suspended try_wait, then sleep
+// between polls -- their spinning took a third of the SM's issue slots away from the decoder warps (profiles/r2v).
+__device__ __forceinline__ void mbar_wait_lazy_a(uint32_t bar_addr, uint32_t parity, unsigned sleep_ns) {
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_addr), "r"(parity), "r"(2000u) : "memory");
+        if (done) break;
+        __nanosleep(sleep_ns);
+    }
+}
 __device__ __forceinline__ void p_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kV2PThreads) : "memory"); }
 
 __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const __grid_constant__ AppMmaArgs args) {
@@ -354,9 +368,10 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
         const bool has_view = a.shading != T2N_SHADE_MLP_FEA_NOVIEW;
         int gi = 0;                                         // basis chunks published so far
         int gdone_known = -1;
+        const uint32_t bars_a = sm_addr + L.bars;
         auto wait_gdone = [&](int p) {
             if (p > gdone_known) {
-                mbar_wait_backoff(bars + kBarGDone + (p & 1), (uint32_t)(p >> 1) & 1u, args.backoff_ns);
+                mbar_wait_lazy_a(bars_a + 8 * (kBarGDone + (p & 1)), (uint32_t)(p >> 1) & 1u, 400u);
                 gdone_known = p;
             }
         };
@@ -477,7 +492,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
             for (int i = 0; i < n_tiles; ++i)
                 for (int c = 0; c < nk0; ++c) {
                     const uint32_t s = gi & 1, ph = (gi >> 1) & 1;
-                    if (c == 0 && i >= 2) mbar_wait_hint_a(bars_addr + 8 * (kBarD0Free + (i & 1)), (uint32_t)((i >> 1) - 1) & 1u, 2000u);
+                    if (c == 0 && i >= 2) mbar_wait_lazy_a(bars_addr + 8 * (kBarD0Free + (i & 1)), (uint32_t)((i >> 1) - 1) & 1u, 100u);
                     mbar_wait_hint_a(bars_addr + 8 * (kBarBbFull + s), ph, 2000u);
                     mbar_wait_hint_a(bars_addr + 8 * (kBarGFull + s), ph, 2000u);
                     tc_fence_after();
@@ -498,7 +513,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
             for (int i = 0; i < n_tiles; ++i)
                 for (int c = 0; c < nk0; ++c) {
                     const uint32_t s = gi & 1;
-                    if (gi >= 2) mbar_wait_hint_a(bars_addr + 8 * (kBarGDone + s), ((gi >> 1) - 1) & 1u, 2000u);
+                    if (gi >= 2) mbar_wait_lazy_a(bars_addr + 8 * (kBarGDone + s), ((gi >> 1) - 1) & 1u, 200u);
                     tma_load_elect(smb + L.bb + s * kV2BasisStage, args.pack + P.basis_off + (size_t)c * 2 * 32 * 32, kV2BasisStage,
                                    bars_addr + 8 * (kBarBbFull + s));
                     ++gi;
@@ -537,7 +552,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
             uint32_t ld = 0;
             auto load = [&](const float* src) {
                 const uint32_t bs = ld & 3;
-                if (ld >= kV2NB) mbar_wait_hint_a(bars_addr + 8 * (kBarPDone + bs), ((ld >> 2) - 1) & 1u, 2000u);
+                if (ld >= kV2NB) mbar_wait_lazy_a(bars_addr + 8 * (kBarPDone + bs), ((ld >> 2) - 1) & 1u, 100u);
                 tma_load_elect(smb + L.pb + bs * kStageB, src, 2 * kTileBytes, bars_addr + 8 * (kBarPbFull + bs));
                 ++ld;
             };
