@@ -327,6 +327,49 @@ def test_backward_mma_steady_state_vs_oracle(cuda_device):
     check_grads(model, {k: v.grad for k, v in p_ref.items()}, kink_samples=kinks)
 
 
+@pytest.mark.parametrize("shading,fea_pe,view_pe,n_app", [("MLP_Fea", 2, 2, (48, 48, 48)), ("MLP_Fea", 6, 6, (48, 32, 48)),
+                                                          ("MLP", 0, 6, (48, 48, 48))])
+def test_mma_view_heads_vs_oracle(shading, fea_pe, view_pe, n_app, cuda_device):
+    """Heads that consume the view direction, inside the tensor-core envelope and with several tiles per CTA: the
+    role-specialised forward kernel carries the direction through the basis GEMM (appearance_mma2.cuh); forward values and
+    all gradients (the backward reads the feature / activation images the forward saved) against the oracle.  The 128-component
+    case has no padding column left in its last basis chunk: the direction takes a chunk of its own."""
+    spec = orc.FieldSpec(aabb=[[-8, -8, -8], [8, 8, 8]], grid=[48, 56, 64], near_far=[0.5, 8.0], step_ratio=1.0,
+                         shading=shading, fea_pe=fea_pe, view_pe=view_pe, app_n_comp=n_app)
+    params = orc.init_params(spec, seed=21, density_gain=5.0, app_gain=3.0)
+    g = torch.Generator().manual_seed(121)
+    R = 6144
+    d = torch.cat([0.5 * (torch.rand(R, 2, generator=g) * 2 - 1), torch.ones(R, 1)], -1)
+    d = d / d.norm(dim=-1, keepdim=True)
+    o = torch.tensor([0.1, 0.0, -0.2]).expand(R, 3) + 0.02 * torch.randn(R, 3, generator=g)
+    rays = torch.cat([o, d], -1).contiguous()
+    jitter = torch.rand(R, 1, generator=g)
+    S = orc.derive_step(spec)[1] // 2
+    rgb_gt = torch.rand(R, 3, generator=g)
+    depth_gt = 0.5 + 7.5 * torch.rand(R, generator=g)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref = orc.render(spec, p_ref, rays, S, True, True, jitter, None, keep=True)
+    loss_ref = orc.training_loss(*ref[:4], rgb_gt, depth_gt)
+    loss_ref.backward()
+    kinks, _ = orc.relu_kink_samples(spec, params, rays, ref[4])
+    model = build_model(spec, params, cuda_device)
+    assert model._mma_pack_buffer(cuda_device, model._native_field()) is not None, "case must be inside the tensor-core envelope"
+    with torch.no_grad():
+        ref_eval = orc.render(spec, params, rays, S, False, True, None)
+        out_eval = model(rays.to(cuda_device), is_train=False, white_bg=True, N_samples=S)
+    _check_forward(out_eval, dict(rgb_map=ref_eval[0], depth_map=ref_eval[1], z_vals=ref_eval[2], weight=ref_eval[3]), w_rtol=2e-4)
+    for _ in range(2):      # the first pass sizes the operand-image capacity (see the steady-state test)
+        model.zero_grad()
+        out = render_with_jitter(model, rays.to(cuda_device), jitter, True, True, S)
+        loss = orc.training_loss(*out, rgb_gt.to(cuda_device), depth_gt.to(cuda_device))
+        loss.backward()
+        torch.cuda.synchronize()
+    _check_forward([t.detach() for t in out], dict(rgb_map=ref[0].detach(), depth_map=ref[1].detach(), z_vals=ref[2].detach(),
+                                                   weight=ref[3].detach()), w_rtol=2e-4)
+    assert abs(float(loss) - float(loss_ref)) <= 2e-5 * abs(float(loss_ref))
+    check_grads(model, {k: v.grad for k, v in p_ref.items()}, kink_samples=kinks)
+
+
 def test_forward_backward_vs_oracle_at_bench_shape(cuda_device):
     """BASELINE configs 2-5's real shape -- 300^3 field, box +-1.5 at z 2.5..5.5, S=1036 -- on 512 random rays of the
     800x800 view: forward (eval and train) and all 19 gradients against the oracle."""

@@ -224,7 +224,8 @@ const char* t2n_error_string(int code) {
 size_t t2n_mma_pack_floats(const T2NField* field) {
     MmaRecipe R;
     if (!field || !mma_recipe(field, R)) return 0;
-    return mma_pack_layout(field->n_app[0] + field->n_app[1] + field->n_app[2], R.Kp).total;
+    return mma_pack_layout(field->n_app[0] + field->n_app[1] + field->n_app[2], R.Kp,
+                           field->shading != T2N_SHADE_MLP_FEA_NOVIEW ? 3 : 0).total;
 }
 
 size_t t2n_bwd_pack_floats(const T2NField* field) {
@@ -331,11 +332,11 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
         const bool use_mma = scratch->mma_pack != nullptr && mma_recipe(field, R);
         if (use_mma) {
             g_prof.start(1, st);
-            // The role-specialised kernel (appearance_mma2.cuh) carries the view direction through the basis GEMM, which needs three
-            // padding columns in the last basis chunk; T2N_APP_V1 / the accuracy-study and trace hooks select the first kernel.
+            // The role-specialised kernel (appearance_mma2.cuh) carries the view direction through the basis GEMM: three extra
+            // columns in the last basis chunk (mma_pack_layout's view_cols).  The first kernel (appearance_mma.cuh) is kept for the
+            // cycle-counter trace and the accuracy-study hook and for A/B timing (T2N_APP_V1); it is never selected otherwise.
             const bool has_view = field->shading != T2N_SHADE_MLP_FEA_NOVIEW;
-            const bool use_v2 = !getenv("T2N_APP_V1") && !getenv("T2N_MMA_TERMS") && !getenv("T2N_MMA_TRACE") &&
-                                (!has_view || (aa.n_app_total % 32) != 0);
+            const bool use_v2 = !getenv("T2N_APP_V1") && !getenv("T2N_MMA_TERMS") && !getenv("T2N_MMA_TRACE");
             rc = launch_pack_mma(aa, R, params->w1, field->mlp_in, scratch->mma_pack, (use_v2 && has_view) ? 1 : 0, st);
             g_prof.stop(st);
             if (rc) return rc;
@@ -343,6 +344,7 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
             memset(&ma2, 0, sizeof(ma2));
             ma2.fw = aa;
             ma2.pack = scratch->mma_pack;
+            ma2.view_cols = (use_v2 && has_view) ? 3 : 0;
             if (scratch->act_h1_img && scratch->act_h2_img && scratch->act_feat && scratch->act_rows >= 128) {
                 ma2.h1_img = scratch->act_h1_img; ma2.h2_img = scratch->act_h2_img; ma2.feat = scratch->act_feat;
                 ma2.act_rows = scratch->act_rows & ~(int64_t)127;
@@ -353,7 +355,7 @@ int t2n_render_forward(const T2NField* field, const T2NParams* params, const T2N
             ma2.terms = tenv ? atoi(tenv) : 7;
             const char* benv = getenv("T2N_MMA_BACKOFF_NS");
             ma2.backoff_ns = benv ? (unsigned)atoi(benv) : 64u;
-            if (getenv("T2N_MMA_TRACE")) {                       // debug cycle counters of CTA 0
+            if (getenv("T2N_MMA_TRACE") || getenv("T2N_V2_TRACE")) {     // debug cycle counters of CTA 0
                 if (!g_trace) cudaMalloc(&g_trace, kTraceLen * sizeof(long long));
                 cudaMemsetAsync(g_trace, 0, kTraceLen * sizeof(long long), st);
                 ma2.trace = g_trace;

@@ -44,7 +44,7 @@ struct PackPerm { short perm[32 * (1 + 2 * kMaxFreq)]; };
 static __global__ void pack_mma_weights_kernel(const float* __restrict__ basis, int app_dim, int n_app_total,
                                                const float* __restrict__ w1, const __grid_constant__ PackPerm perm, int K,
                                                int Kp, const float* __restrict__ w2, float* __restrict__ out, int view_rows) {
-    const MmaPack P = mma_pack_layout(n_app_total, Kp);
+    const MmaPack P = mma_pack_layout(n_app_total, Kp, view_rows ? 3 : 0);
     const int total_groups = (P.basis_chunks * 32 + P.w1_chunks * 128 + P.w2_chunks * 128) * 8;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_groups) return;

@@ -30,6 +30,11 @@ constexpr int kV2PWarps = 8;
 constexpr int kV2GWarps = 16;
 constexpr int kV2PThreads = kV2PWarps * 32;
 constexpr int kV2GThreads = kV2GWarps * 32;
+// Warp order matters (measured, profiles/r2v): with the decoder warps FIRST (0..7) a view takes 36.5 ms, with the gather warps
+// first and the decoder warps at 16..23 it takes 42.2 ms -- the decoder warps are the critical chain and get more issue slots
+// at the low warp ids.
+constexpr int kV2WarpP0 = 0;                           // first decoder warp (a multiple of 4: TMEM lane quarter = warp & 3)
+constexpr int kV2WarpG0 = kV2PWarps;                   // first gather warp
 constexpr int kV2WarpGIssue = kV2PWarps + kV2GWarps;   // 24
 constexpr int kV2WarpGLoad = kV2WarpGIssue + 1;
 constexpr int kV2WarpPIssue = kV2WarpGIssue + 2;
@@ -72,6 +77,48 @@ __host__ __device__ inline V2Smem v2_smem_layout() {
     return L;
 }
 
+// ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100: two IEEE operations per issued instruction) ----------------
+// TF32 split of 8 values, two at a time: hi = top 19 bits, lo = v - hi as one exact FFMA2 (hi * -1 + v)
+__device__ __forceinline__ void split8_x2(const float (&v)[8], uint32_t (&h)[8], uint32_t (&l)[8]) {
+    const float2 m1 = make_float2(-1.f, -1.f);
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        h[k] = tf32_trunc(v[k]); h[k + 1] = tf32_trunc(v[k + 1]);
+        const float2 lo = __ffma2_rn(make_float2(__uint_as_float(h[k]), __uint_as_float(h[k + 1])), m1, make_float2(v[k], v[k + 1]));
+        l[k] = __float_as_uint(lo.x); l[k + 1] = __float_as_uint(lo.y);
+    }
+}
+__device__ __forceinline__ void st_split8_tmem_x2(uint32_t a_stage_lane, int col, const float (&v)[8]) {
+    uint32_t h[8], l[8];
+    split8_x2(v, h, l);
+    tmem_st8(a_stage_lane + col, h);
+    tmem_st8(a_stage_lane + 32 + col, l);
+}
+__device__ __forceinline__ void st_split4_x2(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, float4 v) {
+    const float2 m1 = make_float2(-1.f, -1.f);
+    uint4 h, l;
+    h.x = tf32_trunc(v.x); h.y = tf32_trunc(v.y); h.z = tf32_trunc(v.z); h.w = tf32_trunc(v.w);
+    const float2 l0 = __ffma2_rn(make_float2(__uint_as_float(h.x), __uint_as_float(h.y)), m1, make_float2(v.x, v.y));
+    const float2 l1 = __ffma2_rn(make_float2(__uint_as_float(h.z), __uint_as_float(h.w)), m1, make_float2(v.z, v.w));
+    l.x = __float_as_uint(l0.x); l.y = __float_as_uint(l0.y); l.z = __float_as_uint(l1.x); l.w = __float_as_uint(l1.y);
+    *reinterpret_cast<uint4*>(tile_hi + off) = h;
+    *reinterpret_cast<uint4*>(tile_lo + off) = l;
+}
+// bilinear blend of four texels times the linear blend of two line taps, 4 channels (same operation order as f4_fma / f4_scale)
+__device__ __forceinline__ float4 blend_x2(float w_nw, float w_ne, float w_sw, float w_se, float w_z0, float w_z1, float4 t0,
+                                           float4 t1, float4 t2, float4 t3, float4 l0, float4 l1) {
+    const float2 nw = make_float2(w_nw, w_nw), ne = make_float2(w_ne, w_ne), sw = make_float2(w_sw, w_sw), se = make_float2(w_se, w_se);
+    const float2 z0 = make_float2(w_z0, w_z0), z1 = make_float2(w_z1, w_z1);
+    float2 pa = __fmul2_rn(nw, make_float2(t0.x, t0.y)), pb = __fmul2_rn(nw, make_float2(t0.z, t0.w));
+    pa = __ffma2_rn(ne, make_float2(t1.x, t1.y), pa); pb = __ffma2_rn(ne, make_float2(t1.z, t1.w), pb);
+    pa = __ffma2_rn(sw, make_float2(t2.x, t2.y), pa); pb = __ffma2_rn(sw, make_float2(t2.z, t2.w), pb);
+    pa = __ffma2_rn(se, make_float2(t3.x, t3.y), pa); pb = __ffma2_rn(se, make_float2(t3.z, t3.w), pb);
+    float2 la = __fmul2_rn(z0, make_float2(l0.x, l0.y)), lb = __fmul2_rn(z0, make_float2(l0.z, l0.w));
+    la = __ffma2_rn(z1, make_float2(l1.x, l1.y), la); lb = __ffma2_rn(z1, make_float2(l1.z, l1.w), lb);
+    pa = __fmul2_rn(pa, la); pb = __fmul2_rn(pb, lb);
+    return make_float4(pa.x, pa.y, pb.x, pb.y);
+}
+
 __device__ __forceinline__ uint32_t tmem_ld1_nowait(uint32_t taddr) {
     uint32_t r;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
@@ -109,8 +156,15 @@ __device__ __forceinline__ void mbar_wait_lazy_a(uint32_t bar_addr, uint32_t par
         __nanosleep(sleep_ns);
     }
 }
+__device__ __forceinline__ void g_sync() { asm volatile("bar.sync 2, %0;" :: "n"(kV2GThreads) : "memory"); }
 __device__ __forceinline__ void p_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kV2PThreads) : "memory"); }
 
+// TR: cycle-counter instantiation (tools/trace_mma2.py, T2N_V2_TRACE): CTA 0 accumulates the time each role spends in its waits.
+//   trace[0..7]   decoder warp 0 : total, wait D1 (acc1), wait D0, wait A-stage free, tiles
+//   trace[8..15]  decoder issuer : total, wait A chunk, wait weight chunk, wait D2 free
+//   trace[16..23] gather warp 8  : total, wait stage free, wait D2 (acc2), layer-3 service incl. waits
+//   trace[24..31] basis issuer   : total, wait A chunk, wait weight chunk, wait D0 free
+template <bool TR>
 __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const __grid_constant__ AppMmaArgs args) {
     extern __shared__ uint8_t smem_raw[];
     const AppArgs& a = args.fw;
@@ -119,7 +173,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
     const uint32_t sm_addr = smem_u32(sm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = a.counters[0];
-    const MmaPack P = mma_pack_layout(a.n_app_total, args.Kp);
+    const MmaPack P = mma_pack_layout(a.n_app_total, args.Kp, args.view_cols);
     const int nk0 = P.basis_chunks, nk1 = P.w1_chunks, nk2 = P.w2_chunks;
 
     float* b1s = reinterpret_cast<float*>(sm + L.b1);
@@ -152,10 +206,17 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
 
     int n_tiles = 0;
     for (int tile = blockIdx.x; tile * kMmaM < total; tile += gridDim.x) ++n_tiles;
+    const bool tr_on = TR && args.trace != nullptr && blockIdx.x == 0;
+    long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;
+    const long long t_start = TR ? clock64() : 0;
+    auto timed = [&](long long& acc, auto&& fn) {
+        if (TR) { const long long c0 = clock64(); fn(); acc += clock64() - c0; }
+        else fn();
+    };
 
-    if (warp < kV2PWarps) {
+    if (warp < kV2WarpG0) {
         // =========================== DECODER PRODUCERS / EPILOGUES ===========================
-        const int lq = warp & 3, q = warp >> 2;             // TMEM lane quarter, column half
+        const int lq = warp & 3, q = (warp - kV2WarpP0) >> 2;   // TMEM lane quarter, column half
         const int erow = 32 * lq + lane;                    // row of the tile = TMEM lane
         const uint32_t tmem_lane = (uint32_t)(32 * lq) << 16;
         int it = 0;                                         // decoder chunks published so far
@@ -163,7 +224,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
         int done_known = -1;
         auto wait_done = [&](int p) {
             if (p > done_known) {
-                mbar_wait_hint(bars + kBarPDone + (p & 3), (uint32_t)(p >> 2) & 1u, 1000u);
+                timed(tw2, [&] { mbar_wait_hint(bars + kBarPDone + (p & 3), (uint32_t)(p >> 2) & 1u, 1000u); });
                 done_known = p;
             }
         };
@@ -174,14 +235,28 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                              : "=r"(ok) : "r"(smem_u32(bars + kBarPDone + (p & 3))), "r"((uint32_t)(p >> 2) & 1u) : "memory");
             return ok;
         };
-        auto finish_done = [&](int p, uint32_t ok) {
+        auto finish_done_raw = [&](int p, uint32_t ok) {
             if (!ok) wait_done(p);
             else if (p > done_known) done_known = p;
         };
+        // Publishing is deferred: a chunk's tcgen05.st are left in flight while the next chunk's columns are computed and
+        // the arrival follows just before that chunk's own stores (or before anything that waits for the tensor pipe), so
+        // the completion latency of the stores is not on the decoder warps' critical path.
+        bool pending = false;
+        auto flush = [&]() {
+            if (pending) {
+                timed(tw3, [&] { tmem_st_wait(); });
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(bars + kBarPFull + ((it - 1) & 3));
+                pending = false;
+            }
+        };
+        auto finish_done = [&](int p, uint32_t ok) {     // called right before a chunk's stores
+            flush();
+            finish_done_raw(p, ok);
+        };
         auto publish = [&]() {
-            tmem_st_wait();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(bars + kBarPFull + (it & 3));
+            pending = true;
             ++it;
             st3 = st3 == kTmemAStages - 1 ? 0 : st3 + 1;
         };
@@ -191,13 +266,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
             float h8[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) h8[k] = c[k];
-            st_split8_tmem(ta, 16 * q, h8);
+            st_split8_tmem_x2(ta, 16 * q, h8);
 #pragma unroll
             for (int k = 0; k < 8; ++k) h8[k] = c[8 + k];
-            st_split8_tmem(ta, 16 * q + 8, h8);
+            st_split8_tmem_x2(ta, 16 * q + 8, h8);
         };
         auto acc_wait = [&](int bar, int local_tile) {
-            mbar_wait_hint(bars + bar, (uint32_t)local_tile & 1u, 1000u);
+            flush();
+            timed(tw0, [&] { mbar_wait_hint(bars + bar, (uint32_t)local_tile & 1u, 1000u); });
             tc_fence_after();
         };
 
@@ -207,13 +283,15 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
 
         auto pe_chunk = [&](float (&sn)[8], float (&cs)[8], int f) {
             const uint32_t rdy = poll_done(it - kTmemAStages);
-            if (f > 0) {
+            if (f > 0) {        // angle doubling, two entries per instruction: sin 2x = (2 sin x) cos x, cos 2x = 1 - (2 sin x) sin x
+                const float2 one = make_float2(1.f, 1.f), m2 = make_float2(-2.f, -2.f);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float s2 = 2.f * sn[k];
-                    const float ns = s2 * cs[k];
-                    cs[k] = fmaf(-s2, sn[k], 1.f);
-                    sn[k] = ns;
+                for (int k = 0; k < 8; k += 2) {
+                    const float2 s = make_float2(sn[k], sn[k + 1]), c0 = make_float2(cs[k], cs[k + 1]);
+                    const float2 ms2 = __fmul2_rn(s, m2);               // -2 sin x (exact)
+                    const float2 nc = __ffma2_rn(ms2, s, one);
+                    const float2 ns = __fmul2_rn(__fadd2_rn(s, s), c0);
+                    sn[k] = ns.x; sn[k + 1] = ns.y; cs[k] = nc.x; cs[k + 1] = nc.y;
                 }
             }
             float c[16];
@@ -224,7 +302,10 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
             publish();
         };
 
+        long long ph[5] = {0, 0, 0, 0, 0}, ph_t = TR ? clock64() : 0;    // trace: S2, chunk 0, seeds, PE chunks, S3
+        auto ph_mark = [&](int k) { if (TR) { const long long now = clock64(); ph[k] += now - ph_t; ph_t = now; } };
         for (int i = 0; i <= n_tiles; ++i) {
+            ph_mark(4);
             // ---- S2(i-1): relu(D1 + b1) -> layer-2 A chunks
             if (i >= 1) {
                 const long long e_row = (long long)(blockIdx.x + (i - 1) * gridDim.x) * kMmaM + erow;
@@ -252,9 +333,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                     publish();
                 }
             }
+            ph_mark(0);
             // ---- S1(i): identity columns, PE seeds, frequency chunks
             if (i < n_tiles) {
-                mbar_wait_hint(bars + kBarD0Full + (i & 1), (uint32_t)(i >> 1) & 1u, 1000u);
+                flush();
+                timed(tw1, [&] { mbar_wait_hint(bars + kBarD0Full + (i & 1), (uint32_t)(i >> 1) & 1u, 1000u); });
                 tc_fence_after();
                 const uint32_t d0 = tmem + tmem_lane + kV2ColD0 + 32 * (i & 1);
                 {
@@ -274,6 +357,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                     store16(c);
                     publish();
                 }
+                ph_mark(1);
                 if (args.feat != nullptr) {     // feature vector for the backward's PE chain (tcgen05.ld is warp-collective)
                     const long long e_feat = (long long)(blockIdx.x + i * gridDim.x) * kMmaM + erow;
                     uint32_t v[16];
@@ -307,10 +391,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                         if (args.pe_nf[16 + 8 * q + k] > 0) sincos_pe(__uint_as_float(v[8 + k]), &sn1[k], &cs1[k]);
                     }
                 }
+                ph_mark(2);
                 for (int f = 0; f < args.n_freq; ++f) {
                     pe_chunk(sn0, cs0, f);
                     if (args.pe_chunks == 2) pe_chunk(sn1, cs1, f);
                 }
+                ph_mark(3);
             }
             // ---- S3(i-1): relu(D2 + b2) . W3 + b3 -> sigmoid
             if (i >= 1) {
@@ -347,7 +433,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                 pp[0] = s0; pp[1] = s1; pp[2] = s2;
                 tc_fence_before();
                 p_sync();       // (the buffer written two iterations ago was read before the barrier of the previous iteration)
-                for (int o = tid; o < kMmaM * 3; o += kV2PThreads) {
+                for (int o = tid - kV2WarpP0 * 32; o < kMmaM * 3; o += kV2PThreads) {
                     const int m = o / 3, c = o - m * 3;
                     const long long e = e0 + m;
                     if (e < total) {
@@ -358,9 +444,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                 }
             }
         }
+        if (tr_on && tid == kV2WarpP0 * 32) {
+            args.trace[0] = clock64() - t_start; args.trace[1] = tw0; args.trace[2] = tw1; args.trace[3] = tw2; args.trace[4] = n_tiles;
+            for (int k = 0; k < 5; ++k) args.trace[32 + k] = ph[k];
+            args.trace[5] = tw3;
+        }
     } else if (warp < kV2WarpGIssue) {
         // =========================== GATHER ===========================
-        const int gt = tid - kV2PThreads;
+        const int gt = tid - kV2WarpG0 * 32;
         const int row = gt >> 2, sub = gt & 3;              // 4 threads per sample, 4 channels each per unit
         const int G0 = a.f.G[0], G1 = a.f.G[1], G2 = a.f.G[2];
         const int Un = a.n_app_total >> 4;                  // real gather units (16 channels each)
@@ -371,7 +462,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
         const uint32_t bars_a = sm_addr + L.bars;
         auto wait_gdone = [&](int p) {
             if (p > gdone_known) {
-                mbar_wait_lazy_a(bars_a + 8 * (kBarGDone + (p & 1)), (uint32_t)(p >> 1) & 1u, 400u);
+                timed(tw0, [&] { mbar_wait_lazy_a(bars_a + 8 * (kBarGDone + (p & 1)), (uint32_t)(p >> 1) & 1u, 150u); });
                 gdone_known = p;
             }
         };
@@ -459,9 +550,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                 float4 prod = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (k < Un) {
                     if (live) {
-                        const float4 pv = f4_fma(w_se, pf3, f4_fma(w_sw, pf2, f4_fma(w_ne, pf1, f4_scale(w_nw, pf0))));
-                        const float4 lv = f4_fma(w_z1, pf5, f4_scale(w_z0, pf4));
-                        prod = f4_mul(pv, lv);
+                        prod = blend_x2(w_nw, w_ne, w_sw, w_se, w_z0, w_z1, pf0, pf1, pf2, pf3, pf4, pf5);
                     }
                     if (k + 1 < Un) unit_loads(k + 1);      // next unit's loads fly while this one is split and stored
                 } else if (k == Un) {
@@ -471,7 +560,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                 const int st = gi & 1;
                 if (!(k & 1)) wait_gdone(gi - 2);           // stage free: the basis chunk two back has completed
                 uint8_t* A_hi = sm + L.ga + st * kStageA;
-                st_split4(A_hi, A_hi + kTileBytes, sw128_off(row, (k & 1) * 4 + sub), prod);
+                st_split4_x2(A_hi, A_hi + kTileBytes, sw128_off(row, (k & 1) * 4 + sub), prod);
                 if (k & 1) {
                     fence_async_smem();                     // generic-proxy writes -> async proxy
                     tc_fence_before();
@@ -480,6 +569,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                     ++gi;
                 }
             }
+        }
+        if (tr_on && gt == 0) {
+            args.trace[16] = clock64() - t_start; args.trace[17] = tw0; args.trace[18] = tw1; args.trace[19] = tw2;
         }
     } else if (warp == kV2WarpGIssue) {
         // =========================== BASIS ISSUER ===========================
@@ -492,9 +584,10 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
             for (int i = 0; i < n_tiles; ++i)
                 for (int c = 0; c < nk0; ++c) {
                     const uint32_t s = gi & 1, ph = (gi >> 1) & 1;
-                    if (c == 0 && i >= 2) mbar_wait_lazy_a(bars_addr + 8 * (kBarD0Free + (i & 1)), (uint32_t)((i >> 1) - 1) & 1u, 100u);
-                    mbar_wait_hint_a(bars_addr + 8 * (kBarBbFull + s), ph, 2000u);
-                    mbar_wait_hint_a(bars_addr + 8 * (kBarGFull + s), ph, 2000u);
+                    if (c == 0 && i >= 2)
+                        timed(tw2, [&] { mbar_wait_lazy_a(bars_addr + 8 * (kBarD0Free + (i & 1)), (uint32_t)((i >> 1) - 1) & 1u, 100u); });
+                    timed(tw1, [&] { mbar_wait_hint_a(bars_addr + 8 * (kBarBbFull + s), ph, 2000u); });
+                    timed(tw0, [&] { mbar_wait_hint_a(bars_addr + 8 * (kBarGFull + s), ph, 2000u); });
                     tc_fence_after();
                     const uint32_t ah = desc_lo(smb + L.ga + s * kStageA), al = ah + (kTileBytes >> 4);
                     const uint32_t bh = desc_lo(smb + L.bb + s * kV2BasisStage), bl = bh + ((32 * 128) >> 4);
@@ -503,6 +596,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
                     if (c == nk0 - 1) umma_commit_elect(bars_addr + 8 * (kBarD0Full + (i & 1)));
                     ++gi;
                 }
+            if (tr_on && lane == 0) {
+                args.trace[24] = clock64() - t_start; args.trace[25] = tw0; args.trace[26] = tw1; args.trace[27] = tw2;
+            }
         }
     } else if (warp == kV2WarpGLoad) {
         // =========================== BASIS WEIGHT LOADER ===========================
@@ -529,8 +625,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
             uint32_t it = 0, st3 = 0;
             auto issue = [&](uint32_t d, int c, int len, int acc_bar) {
                 const uint32_t bs = it & 3, ph = (it >> 2) & 1;
-                mbar_wait_hint_a(bars_addr + 8 * (kBarPbFull + bs), ph, 2000u);
-                mbar_wait_hint_a(bars_addr + 8 * (kBarPFull + bs), ph, 2000u);
+                timed(tw1, [&] { mbar_wait_hint_a(bars_addr + 8 * (kBarPbFull + bs), ph, 2000u); });
+                timed(tw0, [&] { mbar_wait_hint_a(bars_addr + 8 * (kBarPFull + bs), ph, 2000u); });
                 tc_fence_after();
                 const uint32_t bh = desc_lo(smb + L.pb + bs * kStageB), bl = bh + (kTileBytes >> 4);
                 umma_ts_chunk_3x(d, tm + kColA + 64 * st3, bh, bl, kDescHi, idesc128, c != 0);
@@ -542,6 +638,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
             for (int i = 0; i <= n_tiles; ++i) {
                 if (i >= 1) for (int c = 0; c < nk2; ++c) issue(tm + kColD2, c, nk2, kBarAcc2);
                 if (i < n_tiles) for (int c = 0; c < nk1; ++c) issue(tm + kColD1, c, nk1, kBarAcc1);
+            }
+            if (tr_on && lane == 0) {
+                args.trace[8] = clock64() - t_start; args.trace[9] = tw0; args.trace[10] = tw1; args.trace[11] = tw2;
             }
         }
     } else {
@@ -563,7 +662,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const _
         }
     }
 
-    // teardown: the decoder warps have waited for the last D2, the last D0 was consumed: every MMA has completed
+    // teardown: the gather warps have waited for the last D2, the last D0 was consumed: every MMA has completed
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {

@@ -162,9 +162,10 @@ struct MmaPack {
     int basis_chunks, w1_chunks, w2_chunks;
     size_t basis_off, w1_off, w2_off, total;     // in floats
 };
-__host__ __device__ inline MmaPack mma_pack_layout(int n_app_total, int Kp) {
+// view_cols: 3 when the basis GEMM also carries the view direction (appearance_mma2.cuh, heads with a view input), else 0
+__host__ __device__ inline MmaPack mma_pack_layout(int n_app_total, int Kp, int view_cols = 0) {
     MmaPack P;
-    P.basis_chunks = (n_app_total + 31) / 32;
+    P.basis_chunks = (n_app_total + view_cols + 31) / 32;
     P.w1_chunks = Kp / 32;
     P.w2_chunks = 4;
     P.basis_off = 0;
@@ -177,6 +178,7 @@ __host__ __device__ inline MmaPack mma_pack_layout(int n_app_total, int Kp) {
 struct AppMmaArgs {
     AppArgs fw;
     const float* pack;      // pre-swizzled weight images (mma_pack_layout)
+    int view_cols;          // layout parameter of `pack` (mma_pack_layout)
     int terms;              // bit0 hi.hi  bit1 lo.hi  bit2 hi.lo  (7 = 3xTF32; other values: accuracy study only)
     int n_freq, pe_chunks, Kp;
     unsigned char ident_src[32];

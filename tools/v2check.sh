@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-v2}
-timeout 420 python -m pytest tests/test_gpu_parity.py -x -q -k "golden or steady or bench_shape or 64cube or edge" 2>&1 | tail -15
+timeout 420 python -m pytest tests/test_gpu_parity.py -x -q -k "golden or steady or bench_shape or 64cube or edge or view_heads" 2>&1 | tail -15
 echo "pytest rc=$?"
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 tail -3 gpurun_out/${TAG}_bench.err
