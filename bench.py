@@ -611,8 +611,9 @@ def main():
                              "L1 data-pipe wavefronts of the bilinear gathers + issue (factors are L2/L1 resident; HBM only "
                              "carries the [R,S] outputs)"),
         "appearance": kernel_line("appearance", kavg["appearance"], kbytes["appearance"], n_app * 20 + factor_bytes * 0.75,
-                                  "producer warps (gather + decoder columns: issue / chunk hand-off latency); tensor pipe and "
-                                  "HBM both have headroom", mma_fwd),
+                                  "decoder warps (8 warps produce the 17 TMEM A chunks of a tile at ~880 cycles per chunk, of which ~450 "
+                                  "are the latencies of the hand-off instructions, against 768 cycles of MMAs: tools/trace_mma2.py); "
+                                  "tensor pipe and HBM both have headroom", mma_fwd),
         "finalize": kernel_line("finalize", kavg["finalize"], kbytes["finalize"], kbytes["finalize"], "hbm"),
     }
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -8,6 +8,6 @@ timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
     python tools/prof_step.py --views 2 --train-batches 2 > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"march_kernel|app_forward_mma_kernel|app_backward_mma_kernel|app_scatter_kernel|wgrad_mma_kernel|ray_backward_kernel" \
+    -k regex:"march_kernel|app_forward_mma2_kernel|app_backward_mma_kernel|app_scatter_kernel|wgrad_mma_kernel|ray_backward_kernel" \
     -c 14 -o gpurun_out/${TAG}_full -f python tools/prof_step.py --views 1 --train-batches 1 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 tail -3 gpurun_out/${TAG}_pytest.log
