@@ -383,6 +383,13 @@ int t2n_debug_mma_recipe(int shading, int app_dim, int fea_pe, int view_pe, int*
 int t2n_debug_mma_bwd_recipe(int shading, int app_dim, int fea_pe, int view_pe, int* out, int cap);
 /* Same, first n entries of the trace buffer (counters + the per-chunk timeline events of three iterations). */
 int t2n_debug_trace_read_n(long long* out, int n);
+
+/*
+ * t2n_debug_v2_plan: resources and protocol constants of the role-specialised appearance kernel for a decoder shape
+ * (21 ints: dynamic shared memory, threads, registers per thread, TMEM columns and map, ring depths, chunk counts per
+ * tile, warps per role, arrival counts of the A-chunk / D0-free barriers).  Host-side model check: tests/test_v2_protocol.py.
+ */
+int t2n_debug_v2_plan(int n_app_total, int Kp, int view_cols, int* out, int cap);
 int t2n_profile_read(int* ids, float* ms, int n);
 
 /* Test aids for the weight-gradient GEMM kernel (csrc/wgrad_mma.cuh), not part of the reference surface.

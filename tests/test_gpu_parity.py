@@ -328,12 +328,14 @@ def test_backward_mma_steady_state_vs_oracle(cuda_device):
 
 
 @pytest.mark.parametrize("shading,fea_pe,view_pe,n_app", [("MLP_Fea", 2, 2, (48, 48, 48)), ("MLP_Fea", 6, 6, (48, 32, 48)),
-                                                          ("MLP", 0, 6, (48, 48, 48))])
+                                                          ("MLP", 0, 6, (48, 48, 48)), ("MLP_Fea", 3, 3, (64, 48, 48)),
+                                                          ("MLP_Fea_noview", 4, 0, (16, 16, 16))])
 def test_mma_view_heads_vs_oracle(shading, fea_pe, view_pe, n_app, cuda_device):
     """Heads that consume the view direction, inside the tensor-core envelope and with several tiles per CTA: the
     role-specialised forward kernel carries the direction through the basis GEMM (appearance_mma2.cuh); forward values and
-    all gradients (the backward reads the feature / activation images the forward saved) against the oracle.  The 128-component
-    case has no padding column left in its last basis chunk: the direction takes a chunk of its own."""
+    all gradients (the backward reads the feature / activation images the forward saved) against the oracle.  The 128- and
+    160-component cases have no padding column left in their last basis chunk: the direction takes a chunk of its own (six
+    basis chunks at 160); the 48-component case runs two basis chunks per tile."""
     spec = orc.FieldSpec(aabb=[[-8, -8, -8], [8, 8, 8]], grid=[48, 56, 64], near_far=[0.5, 8.0], step_ratio=1.0,
                          shading=shading, fea_pe=fea_pe, view_pe=view_pe, app_n_comp=n_app)
     params = orc.init_params(spec, seed=21, density_gain=5.0, app_gain=3.0)

@@ -128,6 +128,7 @@ SYMBOLS = {
     "t2n_debug_trace_read": (C.c_int, [C.POINTER(C.c_longlong)]),
     "t2n_debug_trace_read_n": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "t2n_debug_chunk_program": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int]),
+    "t2n_debug_v2_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "t2n_debug_mma_recipe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "t2n_debug_mma_bwd_recipe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "t2n_profile_read": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),

@@ -460,6 +460,14 @@ int t2n_debug_chunk_program(int n_app_total, int Kp, unsigned char* out, int cap
     return build_program(out, P.basis_chunks, P.w1_chunks, P.w2_chunks);
 }
 
+int t2n_debug_v2_plan(int n_app_total, int Kp, int view_cols, int* out, int cap) {
+    if (!out || cap < 21 || n_app_total <= 0 || Kp < 32 || (Kp & 31)) return T2N_E_BADARG;
+    int v[21];
+    v2_plan(n_app_total, Kp, view_cols, v);
+    for (int i = 0; i < 21; ++i) out[i] = v[i];
+    return 21;
+}
+
 int t2n_adam_step(const T2NAdamTensor* tensors, int n_tensors, float beta1, float beta2, float eps, float weight_decay,
                   int step, t2n_stream_t stream) {
     if (!tensors || n_tensors < 0 || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f))

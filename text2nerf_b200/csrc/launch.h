@@ -18,6 +18,7 @@ int launch_app_forward(const AppArgs& a, int nq, int smem_bytes, int grid, cudaS
 int launch_app_forward_mma(const AppMmaArgs& a, int smem_bytes, int grid, cudaStream_t st);
 int launch_app_forward_mma2(const AppMmaArgs& a, int smem_bytes, int grid, cudaStream_t st);
 int app_forward_mma2_smem_bytes();
+void v2_plan(int n_app_total, int Kp, int view_cols, int* out21);
 int launch_pack_mma(const AppArgs& a, const MmaRecipe& R, const float* w1, int K, float* out, int view_rows, cudaStream_t st);
 int launch_pack_w1(const float* w1, const int32_t* perm, int C, int K, int Kp, float* w1p, cudaStream_t st);
 int launch_ray_backward(const RayBwdArgs& a, int nq, int smem_bytes, int grid, cudaStream_t st);
