@@ -24,8 +24,12 @@ def test_fused_adam_follows_torch_adam(cuda_device):
             for g in opt.param_groups:
                 g["lr"] = g["lr"] * 0.9
     torch.cuda.synchronize()
+    # The two models get their gradients from two runs of the same kernels, whose `red.global.add` accumulation order is
+    # not deterministic (~1e-7 relative noise per gradient); Adam's g / sqrt(v) normalisation turns that into up to
+    # ~2.5e-5 of the tensor scale on the first decoder matrix after four steps (1 run in 6 on B200).  The optimiser
+    # arithmetic itself is pinned to 2e-6 by the deterministic single-step test below.
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
-        assert scaled_err(pa, pb) <= 2e-5, (k, scaled_err(pa, pb))
+        assert scaled_err(pa, pb) <= 1e-4, (k, scaled_err(pa, pb))
         # the update is visible: parameters moved away from the initial state
     moved = sum(float((p.detach().cpu() - c.params[k]).abs().max()) > 0 for k, p in a.named_parameters())
     assert moved == len(c.params)
