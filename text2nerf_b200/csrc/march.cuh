@@ -160,15 +160,32 @@ __global__ void __launch_bounds__(256) march_kernel(const __grid_constant__ Marc
         float acc = 0.f, dsum = 0.f;
         int n_app = 0;
 
+        // Once the ray has left the box it stays outside: z grows with k and every rounded operation of o + d * z is
+        // monotone, so each coordinate of the sample point is a monotone sequence and "inside" is an interval of k.  A pass
+        // with no sample inside after a pass that had one ends the interval; the remaining passes only write what the
+        // composite of invalid samples produces (z, weight 0, feature -inf, transmittance = carry) -- bit-identical, without
+        // the point / footprint arithmetic, the exp and the product scan (45 % of the passes of the 800x800 bench view).
+        bool seen_inside = false, gone = false;
         for (int base = 0; base < S; base += 32) {
             const int k = base + lane;
             const bool in = k < S;
+            if (gone) {
+                if (in) {
+                    a.z_vals[row + k] = sample_z(f, rs, k, jit, train);
+                    a.weight[row + k] = 0.f;
+                    if (a.sigma_feat) a.sigma_feat[row + k] = -CUDART_INF_F;
+                    if (a.trans) a.trans[row + k] = carry;
+                }
+                continue;
+            }
             // ---- sample phase
             const float z = sample_z(f, rs, k, jit, train);
             const float zn = sample_z(f, rs, k + 1, jit, train);
             float p[3];
             sample_point(rs, z, p);
             bool valid = in && inside_box(f, p);
+            if (__ballot_sync(T2N_FULL, valid)) seen_inside = true;
+            else if (seen_inside) gone = true;              // takes effect from the next pass; this one has no valid sample
             if (valid && f.mask != nullptr) valid = mask_lookup(f, p) > 0.f;
             if (!train) valid = valid && (p[2] > f.z_min);
             const SampleGeom g = sample_geom(f, p);

@@ -873,6 +873,10 @@ class TensorBase(torch.nn.Module):
         # listed samples PER RAY seen recently (decaying maximum), so that a change of batch size scales the estimate
         per_ray = getattr(self, "_listed_per_ray", 0.0)
         rows = max(int(1.25 * per_ray * R) + 1024, 8192) if per_ray > 0 else max(96 * R, 8192)
+        # quantised to eighths of an octave: the estimate moves a little from call to call, and differently sized multi-GB
+        # requests would defeat the caching allocator's block reuse
+        step = max(128, 1 << max(rows.bit_length() - 4, 7))
+        rows = (rows + step - 1) // step * step
         rows = min(rows, R * S, int(os.environ.get("T2N_ACT_ROWS_MAX", 6 << 20)))
         return max(128, (rows + 127) // 128 * 128)
 
