@@ -167,12 +167,15 @@ __global__ void __launch_bounds__(128, 4) ray_backward_kernel(const __grid_const
             const int k = base + lane;
             const bool in = k < S;
             float z = 0.f, zn = 0.f, w = 0.f, T = 0.f, sf = -CUDART_INF_F, gwt = 0.f;
+            if (in) sf = __ldg(a.sigma_feat + row + k);
+            // a pass without a valid sample (outside the box / masked: 45 % of the passes of a lego-shaped batch) has only
+            // zero weights: nothing to scatter, no listed sample, the suffix sum does not change
+            if (!__ballot_sync(T2N_FULL, in && (sf > -CUDART_INF_F))) continue;
             if (in) {
                 z = __ldg(a.z_vals + row + k);
                 zn = (k < S - 1) ? __ldg(a.z_vals + row + k + 1) : z;
                 w = __ldg(a.weight + row + k);
                 T = __ldg(a.trans + row + k);
-                sf = __ldg(a.sigma_feat + row + k);
                 if (a.g_weight) gwt = __ldg(a.g_weight + row + k);
                 else if (a.gw_coef) gwt = (__fadd_rn(__fsub_rn(z, gt_depth), a.delta) < 0.f) ? gw_c : 0.f;
             }
