@@ -416,7 +416,7 @@ def test_forward_backward_vs_oracle_at_bench_shape(cuda_device):
     loss_ref.backward()
     assert abs(float(loss) - float(loss_ref)) <= 2e-5 * abs(float(loss_ref))
     # this seed has one listed sample (ray 229, k = 62, weight 0.068) whose hidden unit 40 of layer 1 sits at
-    # h1 = -1.6e-6: the tensor-core decoder lands on the other side of the kink (tools/diag_bisect.py)
+    # h1 = -1.6e-6: the tensor-core decoder lands on the other side of the kink
     kinks, w_max = orc.relu_kink_samples(spec, params, rays, ref_t[4])
     assert kinks >= 1
     check_grads(model, {k: v.grad for k, v in p_ref.items()}, kink_samples=kinks)
