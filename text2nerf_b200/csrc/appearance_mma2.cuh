@@ -156,13 +156,12 @@ __device__ __forceinline__ void mbar_wait_lazy_a(uint32_t bar_addr, uint32_t par
         __nanosleep(sleep_ns);
     }
 }
-__device__ __forceinline__ void g_sync() { asm volatile("bar.sync 2, %0;" :: "n"(kV2GThreads) : "memory"); }
 __device__ __forceinline__ void p_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kV2PThreads) : "memory"); }
 
 // TR: cycle-counter instantiation (tools/trace_mma2.py, T2N_V2_TRACE): CTA 0 accumulates the time each role spends in its waits.
 //   trace[0..7]   decoder warp 0 : total, wait D1 (acc1), wait D0, wait A-stage free, tiles
 //   trace[8..15]  decoder issuer : total, wait A chunk, wait weight chunk, wait D2 free
-//   trace[16..23] gather warp 8  : total, wait stage free, wait D2 (acc2), layer-3 service incl. waits
+//   trace[16..23] gather warp 8  : total, wait stage free
 //   trace[24..31] basis issuer   : total, wait A chunk, wait weight chunk, wait D0 free
 template <bool TR>
 __global__ void __launch_bounds__(kV2Threads, 1) app_forward_mma2_kernel(const __grid_constant__ AppMmaArgs args) {

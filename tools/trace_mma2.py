@@ -33,8 +33,8 @@ v = list(buf)
 nt = max(v[4], 1)
 print("tiles of CTA 0:", v[4])
 print("decoder warp 0 : %6.0f cyc/tile | wait D1 %6.0f  wait D0 %6.0f  wait A stage %6.0f" % tuple(x / nt for x in v[0:4]))
-print("decoder issuer : %6.0f cyc/tile | wait A chunk %6.0f  wait weights %6.0f  wait D2 free %6.0f" % tuple(x / nt for x in v[8:12]))
-print("gather warp 8  : %6.0f cyc/tile | wait stage %6.0f  wait D2 %6.0f  layer-3 service %6.0f" % tuple(x / nt for x in v[16:20]))
+print("decoder issuer : %6.0f cyc/tile | wait A chunk %6.0f  wait weights %6.0f" % tuple(x / nt for x in v[8:11]))
+print("gather warp 8  : %6.0f cyc/tile | wait stage %6.0f" % tuple(x / nt for x in v[16:18]))
 print("basis issuer   : %6.0f cyc/tile | wait A chunk %6.0f  wait weights %6.0f  wait D0 free %6.0f" % tuple(x / nt for x in v[24:28]))
 print("decoder warp 0 phases per tile: S2 %6.0f  chunk 0 %6.0f  seeds %6.0f  PE chunks %6.0f  S3 %6.0f" % tuple(x / nt for x in v[32:37]))
 print("decoder warp 0: tcgen05.wait::st %6.0f cyc/tile" % (v[5] / nt))
