@@ -197,3 +197,32 @@ def test_fused_training_paths_refuse_cpu_tensors_and_generic_tv_callables_stay_t
     assert torch.equal(m.TV_loss_density(TVLoss()), want)                 # CPU planes: no kernel route
     assert torch.equal(m.TV_loss_density(orc.tv_plane), want)
     assert torch.equal(m.TV_loss_app(lambda x: x.abs().mean()), sum(pl.abs().mean() * 1e-2 for pl in m.app_plane))
+
+
+def test_tf32_round_bit_pattern_is_round_to_nearest_ties_away():
+    """csrc/operand_image.cuh tf32_hi: (bits + 0x1000) & 0xffffe000 is cvt.rna.tf32.f32 (round to nearest, ties away from
+    zero, onto 10 explicit mantissa bits) for every finite input; checked against exact rational arithmetic."""
+    import numpy as np
+    from fractions import Fraction
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 2 ** 32, size=20000, dtype=np.uint64).astype(np.uint32)
+    # add the interesting patterns: ties, all-ones mantissas (carry into the exponent), tiny and huge exponents
+    extra = [0x3f800000 | 0x1000, 0x3f800000 | 0x0fff, 0x3f800000 | 0x1001, 0x3fffffff, 0x3f7ff000, 0xbf801000, 0x00801000,
+             0x7e7ff000, 0x3f803000, 0xbf802fff]
+    bits = np.concatenate([bits, np.array(extra, dtype=np.uint32)])
+    expo = (bits >> 23) & 0xff
+    bits = bits[(expo != 0) & (expo != 255)]                       # normal numbers (the kernels never split inf / nan / denormals)
+    got = ((bits.astype(np.uint64) + 0x1000) & 0xffffe000).astype(np.uint32)
+    for b, g in zip(bits.tolist()[:3000] + bits.tolist()[-len(extra):], got.tolist()[:3000] + got.tolist()[-len(extra):]):
+        x = Fraction(float(np.array([b], dtype=np.uint32).view(np.float32)[0]))
+        e = ((b >> 23) & 0xff) - 127
+        ulp = Fraction(2) ** (e - 10)                               # TF32 keeps 10 mantissa bits
+        qf = abs(x) / ulp
+        n = qf.numerator // qf.denominator
+        if qf - n >= Fraction(1, 2):
+            n += 1                                                  # ties away from zero
+        want = n * ulp * (-1 if x < 0 else 1)
+        gv = np.array([g], dtype=np.uint32).view(np.float32)[0]
+        if np.isfinite(gv):
+            assert Fraction(float(gv)) == want, hex(b)
+        assert g & 0x1fff == 0
